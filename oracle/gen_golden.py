@@ -1,0 +1,141 @@
+"""Generate ``tests/golden/*.npz`` by running the UNMODIFIED reference solver
+(``solver_default``) -- TEST INFRASTRUCTURE ONLY, runs in the build container
+where ``/root/reference`` is mounted:
+
+    python -m oracle.gen_golden            # from the repo root
+
+Each fixture stores the *inputs* a solver needs (mesh lines, float32 inclusion
+list, scaled property tables, courant number, source) and the reference's
+*outputs* (final ux/uy/uz, T1..T6 of the last step, material id map, dt,
+snapshots of the surface uz after selected steps).  The fixtures travel to the
+GPU box, the reference does not.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+from oracle import refshim
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+
+def _run(grid, material, cfg, steps, snaps=()):
+    s = refshim.default_solver()
+    s.cfg.update(cfg)
+    s.cfg["write_mode"] = "off"
+    s.init(grid, material, steps)
+    snaps = sorted(set(snaps))
+    frames = {}
+    # drive the reference loop one step at a time through its own methods, in its own order
+    # (base_solver.py:245-260) so that intermediate surface frames can be captured.
+    wave_fn = {"sin": s.update_sin, "ricker": s.update_ricker}[s.cfg["wave"]]
+    for tt in range(steps):
+        s.g.uz[0, :, 0] = wave_fn(tt=tt, **s.cfg["wave_args"])
+        s.update_T()
+        s.update_T_BC()
+        s.update_u()
+        s.update_u_BC()
+        s.time_step()
+        if (tt + 1) in snaps:
+            frames[tt + 1] = (s.g.ux[:, :, 0].copy(), s.g.uy[:, :, 0].copy(), s.g.uz[:, :, 0].copy())
+    return s, frames
+
+
+def _pack(name, s, frames, steps, courant, extra=None):
+    g, m = s.g, s.m
+    # primary = value at a cell that is never an inclusion; ids from P/C comparison
+    prim_c, sec_c = np.array(m.primary["c"], float), np.array(m.secondary["c"], float)
+    prim_p, sec_p = float(m.primary["p"]), float(m.secondary["p"])
+    if prim_p != sec_p:
+        ids = (m.P == sec_p).astype(np.uint8)
+    else:
+        ids = np.zeros(m.P.shape, np.uint8)
+    assert np.array_equal(np.where(ids[..., None, None] == 1, sec_c, prim_c), m.C)
+    targets = np.array([[t["x"], t["y"], t["z"], t["r"]] for t in m.grid.targets], np.float32).reshape(-1, 4)
+    d = dict(
+        x=g.x, y=g.y, z=g.z, targets=targets,
+        prim_c=prim_c, prim_p=prim_p, sec_c=sec_c, sec_p=sec_p,
+        courant=float(courant), dt=float(m.dt), steps=int(steps),
+        wave=str(s.cfg["wave"]), wave_args=json.dumps(s.cfg["wave_args"]),
+        ids=ids, ux=g.ux, uy=g.uy, uz=g.uz,
+        T1=g.T1, T2=g.T2, T3=g.T3, T4=g.T4, T5=g.T5, T6=g.T6,
+        ux_old=g.ux_old, uy_old=g.uy_old, uz_old=g.uz_old,
+        snap_steps=np.array(sorted(frames), np.int64),
+    )
+    for k, (sx, sy, sz) in frames.items():
+        d["snap_ux_%d" % k], d["snap_uy_%d" % k], d["snap_uz_%d" % k] = sx, sy, sz
+    if extra:
+        d.update(extra)
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **d)
+    print("%-22s grid %s steps %d dt %.17g |uz| %.17g  -> %s (%.0f KB)" % (
+        name, m.P.shape, steps, m.dt, np.linalg.norm(g.uz), os.path.relpath(path), os.path.getsize(path) / 1024))
+
+
+def case_testdefaults():
+    """Solver.test(): TestDefaults grid, 10 steps, ricker (base_solver.py:28-70,286-292)."""
+    refshim.install()
+    from simulation import base_solver
+    s, fr = _run(base_solver.TestDefaults.g, base_solver.TestDefaults.m, {"wave": "ricker", "wave_args": {"f": 100}}, 10, snaps=(1, 10))
+    _pack("testdefaults", s, fr, 10, s.m.c_max)
+
+
+def case_settings(name, path, steps, snaps, cfg_over=None):
+    common = refshim.install()
+    common.findSolvers()
+    cfg, g, m = common.loadSettings(path)
+    scfg = dict(cfg["simulation"]["cfg"])
+    scfg.update(cfg_over or {})
+    s, fr = _run(g, m, scfg, steps, snaps)
+    _pack(name, s, fr, steps, cfg["simulation"]["courant"])
+
+
+def case_custom(name, size, max_d, min_d, incl, steps, snaps, wave, wave_args, courant=0.1,
+                primary="GaAs", secondary="Au"):
+    common = refshim.install()
+    from simulation import grid as rgrid, material as rmat
+    props = json.load(open(os.path.join(refshim.REF_ROOT, "data", "default.json")))["material"]["properties"]
+    g = rgrid.Grid()
+    g.init(size_x=size[0], size_y=size[1], size_z=size[2])
+    g.min_d = min_d
+    g.max_dx, g.max_dy, g.max_dz = max_d
+    g.slope = 1.0
+    for (x, y, z, r) in incl:
+        g.addInclusion(x=x, y=y, z=z, r=r)
+    g.buildMesh()
+    g.update()
+    m = rmat.Material()
+    m.init(grid=g, properties=props)
+    m.c_max = courant
+    m.setPrimary(primary)
+    m.setSecondary(secondary)
+    m.update()
+    s, fr = _run(g, m, {"wave": wave, "wave_args": wave_args}, steps, snaps)
+    _pack(name, s, fr, steps, courant)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    ref = refshim.REF_ROOT
+    case_testdefaults()
+    case_settings("default_json_1000", os.path.join(ref, "data", "default.json"), 1000, (1, 2, 3, 10, 100, 1000))
+    case_settings("nonuniform_json_200", os.path.join(ref, "tests", "data", "nonuniform.json"), 200, (1, 50, 200))
+    case_settings("fine_json_200", os.path.join(ref, "tests", "data", "fine.json"), 200, (200,))
+    # homogeneous GaAs cube, the shape of BASELINE config #2 at reduced size
+    case_custom("homog_32_20", (31, 31, 31), (1, 1, 1), 1, [], 20, (5, 20), "sin", {"f": 100}, secondary="GaAs")
+    # partial-depth inclusions with dz = 0.5: exercises the z re-binding quirk of
+    # inclusionIndices (grid.py:173) and a delayed ricker source
+    case_custom("partial_depth_dz05", (24, 20, 6), (1, 1, 0.5), 0.5,
+                [(8.0, 10.0, 3.0, 2.5), (17.0, 9.0, 2.0, 2.0)], 60, (1, 60), "ricker",
+                {"f": 2000, "source_delay": 2e-4}, secondary="Al")
+    # small crystal, the shape of BASELINE config #3 at reduced size (uniform integer mesh)
+    case_custom("crystal_48x32x12", (47, 31, 11), (1, 1, 1), 1,
+                [(8.0 + 16 * a, 8.0 + 16 * b, 11.0, 4.0) for a in range(3) for b in range(2)][:5],
+                80, (1, 80), "sin", {"f": 100})
+
+
+if __name__ == "__main__":
+    sys.exit(main())

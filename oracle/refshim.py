@@ -1,0 +1,80 @@
+"""Import the UNMODIFIED reference solver in the build container -- TEST INFRASTRUCTURE ONLY.
+
+``/root/reference`` exists only in the build container, never on the GPU box, so
+this module is used by ``oracle/gen_golden.py`` (fixture generation) and by the
+CPU-only tests that are skipped when the reference is absent.  Nothing in the
+product imports it.
+
+Three shims, no edits to the reference:
+  1. stub ``PyQt5.QtCore`` (``gui/worker.py`` only needs QObject/QRunnable/pyqtSignal/pyqtSlot)
+  2. stub ``h5py`` (the oracle always runs with ``write_mode='off'``)
+  3. ``numpy.float = float`` (removed in NumPy >= 1.24, used at grid.py:258,301)
+"""
+import os
+import sys
+import types
+
+import numpy as np
+
+REF_ROOT = os.environ.get("PHONOMENA_REF", "/root/reference")
+
+
+def available():
+    return os.path.isdir(os.path.join(REF_ROOT, "phonomena", "simulation"))
+
+
+class _Signal:
+    def __init__(self, *a, **k):
+        pass
+
+    def emit(self, *a, **k):
+        pass
+
+    def connect(self, *a, **k):
+        pass
+
+
+def install():
+    """Make ``import common`` / ``from simulation import ...`` resolve to the reference."""
+    if not available():
+        raise RuntimeError("reference checkout not present at %s" % REF_ROOT)
+    if not hasattr(np, "float"):
+        np.float = float
+    if "PyQt5" not in sys.modules:
+        qt, qc = types.ModuleType("PyQt5"), types.ModuleType("PyQt5.QtCore")
+
+        class QObject:
+            def __init__(self, *a, **k):
+                pass
+
+        class QRunnable(QObject):
+            pass
+
+        qc.QObject, qc.QRunnable = QObject, QRunnable
+        qc.pyqtSignal = lambda *a, **k: _Signal()
+        qc.pyqtSlot = lambda *a, **k: (lambda f: f)
+        qt.QtCore = qc
+        sys.modules["PyQt5"], sys.modules["PyQt5.QtCore"] = qt, qc
+    if "h5py" not in sys.modules:
+        h5 = types.ModuleType("h5py")
+
+        def _file(*a, **k):
+            raise RuntimeError("h5py is stubbed: run the reference with write_mode='off'")
+
+        h5.File = _file
+        h5.__stub__ = True
+        sys.modules["h5py"] = h5
+    pkg = os.path.join(REF_ROOT, "phonomena")
+    if pkg not in sys.path:
+        sys.path.insert(0, pkg)
+    import common  # noqa: F401  (reference module)
+    return common
+
+
+def default_solver():
+    """A fresh reference ``solver_default.Solver`` with the writer off."""
+    install()
+    from simulation.solvers import solver_default
+    s = solver_default.Solver()
+    s.cfg["write_mode"] = "off"
+    return s
