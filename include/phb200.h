@@ -1,0 +1,148 @@
+/* phb200.h -- C ABI of libphb200.so, the B200 (sm_100a) FDTD time-stepping engine that
+ * replaces the NumPy hot path of Phonomena's solver plugin.
+ *
+ * The reference has no FFI: its path is Python/NumPy inside BaseSolver
+ * (phonomena/simulation/base_solver.py).  Each entry point below names the reference
+ * code it replaces ("replaces:").  The Python plugin `phonomena_b200/solver_b200.py`
+ * (class Solver, same interface as base_solver.BaseSolver) is the only intended caller
+ * and binds these with ctypes; INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *  - All functions return 0 on success, non-zero on error; phb_last_error() gives the
+ *    message for the calling thread.  There is NO CPU fallback: without a CUDA device
+ *    phb_create fails.
+ *  - Host arrays are float64 (the reference's DTYPE, grid.py:21) in the reference's
+ *    C-order shapes: ux (Nx-1,Ny,Nz), uy (Nx,Ny-1,Nz), uz (Nx,Ny,Nz-1)  (grid.py:88-102).
+ *    The library owns its device memory and copies during the call; the caller may
+ *    free its arrays as soon as the call returns.
+ *  - A context may own the whole grid or one x-slab [x0, x0+nxl) of it (one process per
+ *    GPU).  Slab-local host arrays hold only the owned planes: for ux the planes
+ *    x0 .. min(x0+nxl, Nx-1)-1, for uy/uz the planes x0 .. x0+nxl-1.
+ *  - Thread-safety: a context may be used from any host thread, one call at a time
+ *    (the GUI calls init() and run() from different threads, main_widget.py:119-131).
+ */
+#ifndef PHB200_H
+#define PHB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PHB_VERSION 100
+
+typedef struct phb_ctx phb_ctx;
+
+enum { PHB_F32 = 0, PHB_F64 = 1 };
+/* arithmetic mode.
+ *  PHB_FAST : reciprocal spacings, FMA contraction allowed (fp64: <= 1e-12 rel-L2 of the reference)
+ *  PHB_EXACT: true IEEE division, the reference's expression order, no contraction:
+ *             fp64 results are BIT-IDENTICAL to the reference's NumPy evaluation. */
+enum { PHB_FAST = 0, PHB_EXACT = 1 };
+/* stencil kernel selection */
+enum { PHB_KERNEL_AUTO = 0, PHB_KERNEL_NAIVE = 1, PHB_KERNEL_MARCH = 2 };
+/* which displacement buffer */
+enum { PHB_CUR = 0, PHB_OLD = 1 };
+/* surface components to record (bit mask) */
+enum { PHB_REC_UX = 1, PHB_REC_UY = 2, PHB_REC_UZ = 4 };
+
+typedef struct phb_cfg {
+    int32_t nx, ny, nz;      /* global grid points: grid.x.size, grid.y.size, grid.z.size        */
+    int32_t x0, nxl;         /* owned x-planes [x0, x0+nxl); whole grid: x0 = 0, nxl = nx         */
+    int32_t dtype;           /* PHB_F32 | PHB_F64: storage and arithmetic type on the device      */
+    int32_t arith;           /* PHB_FAST | PHB_EXACT                                              */
+    int32_t device;          /* CUDA device ordinal                                               */
+    int32_t kernel;          /* PHB_KERNEL_*                                                      */
+    int32_t record_mask;     /* PHB_REC_* bits; 0 = no surface recording                          */
+    int32_t record_every;    /* record the k=0 plane after every n-th step (>=1)                  */
+    int32_t ring_slots;      /* pinned-host ring depth (frames); 0 = default                      */
+    int32_t reserved[4];
+    double  dt;              /* material.dt                                      (material.py:80-93) */
+    double  d2;              /* dt**2 as evaluated by the host (base_solver.py:443: self.m.dt**2) */
+} phb_cfg;
+
+int         phb_version(void);
+const char *phb_last_error(void);
+int         phb_device_count(int *n);
+
+/* replaces: BaseSolver.init's field allocation via Grid.update (grid.py:79-110): all
+ * displacement buffers start at zero. */
+int phb_create(const phb_cfg *cfg, phb_ctx **out);
+int phb_destroy(phb_ctx *ctx);
+
+/* replaces: use of grid.fdx/fdy/fdz/sdx/sdy/sdz (grid.py:118-127) in every update.
+ * Global arrays of lengths nx-1, ny-1, nz-1, nx-2, ny-2, nz-2. */
+int phb_set_spacing(phb_ctx *ctx, const double *fdx, const double *fdy, const double *fdz,
+                    const double *sdx, const double *sdy, const double *sdz);
+
+/* replaces: Material.C / Material.P as a table: nmat materials, each the 12 stiffness
+ * entries the path reads -- C[r][c] for r,c in 0..2 (row-major, NOT symmetrised), then
+ * C[3][3], C[4][4], C[5][5] -- and the density (material.py:55-63). */
+int phb_set_material_table(phb_ctx *ctx, int32_t nmat, const double *c12, const double *rho);
+
+/* per-cell material id (index into the table), reference layout (planes, Ny, Nz) uint8,
+ * for planes x0 .. min(x0+nxl+1, nx)-1  (one extra plane to the right when it exists). */
+int phb_set_material_ids(phb_ctx *ctx, const uint8_t *ids, int64_t nplanes);
+
+/* replaces: Grid.inclusionIndices + Material.setConstants (grid.py:158-175,
+ * material.py:55-63) evaluated on the device with the same float32/float64 mixing and the
+ * same z re-binding quirk: id 0 everywhere, id 1 inside the cylinders.
+ * targets: n x 4 float32 (x, y, z, r); x, y, z: global mesh lines. */
+int phb_gen_material_ids(phb_ctx *ctx, const float *targets, int32_t n,
+                         const double *x, const double *y, const double *z);
+/* owned planes x0..x0+nxl-1, layout (nxl, Ny, Nz) */
+int phb_get_material_ids(phb_ctx *ctx, uint8_t *ids);
+
+/* replaces: coefficient evaluation at the top of apply_u_abc (base_solver.py:525-537).
+ * coef = { clx, ctx, cly0, cty0, cly1, cty1, clz, ctz } computed by the host exactly as there. */
+int phb_set_abc(phb_ctx *ctx, const double coef[8]);
+
+/* replaces: wave_fn(tt) (base_solver.py:251,294-312): w[tt] for tt = 0..n-1, evaluated by the
+ * host with the reference's own expression. */
+int phb_set_source_table(phb_ctx *ctx, const double *w, int64_t n);
+
+/* field transfer (tests, restart, full-field output); which = PHB_CUR | PHB_OLD.
+ * Any pointer may be NULL to skip that component. */
+int phb_set_fields(phb_ctx *ctx, int32_t which, const double *ux, const double *uy, const double *uz);
+int phb_get_fields(phb_ctx *ctx, int32_t which, double *ux, double *uy, double *uz);
+
+/* debug/parity: the six stress arrays the reference would hold for the displacement
+ * buffer `which` (T1..T3 (n,Ny,Nz), T4 (n,Ny-1,Nz-1), T5 (n',Ny,Nz-1), T6 (n',Ny-1,Nz);
+ * owned planes).  After k steps, which = PHB_OLD reproduces grid.T1..T6. */
+int phb_get_stress(phb_ctx *ctx, int32_t which, double *T1, double *T2, double *T3,
+                   double *T4, double *T5, double *T6);
+
+/* replaces: the body of the time loop (base_solver.py:251-256) for nsteps steps:
+ * source, update_T, update_T_BC, update_u, update_u_BC, time_step [, halo exchange, record].
+ * Enqueues on the context's stream and returns; phb_sync waits. */
+int phb_run(phb_ctx *ctx, int64_t nsteps);
+int phb_sync(phb_ctx *ctx);
+/* same, bracketed by CUDA events on the launching stream; returns elapsed ms */
+int phb_run_timed(phb_ctx *ctx, int64_t nsteps, float *ms);
+int phb_steps_done(phb_ctx *ctx, int64_t *tt);
+/* number of kernels launched by this context so far */
+int phb_launch_count(phb_ctx *ctx, int64_t *n);
+/* name of the stencil kernel variant in use, and device bytes allocated */
+int phb_info(phb_ctx *ctx, char *kernel_name, int32_t len, int64_t *device_bytes);
+
+/* multi-GPU (one process per GPU): NCCL communicator over the slab chain.
+ * replaces: nothing (the reference has no domain decomposition). */
+int phb_comm_unique_id(char id[128]);
+int phb_comm_init(phb_ctx *ctx, const char id[128], int32_t rank, int32_t nranks);
+
+/* surface recording: replaces Grid.freezeData + Writer.put (grid.py:68-77,
+ * base_solver.py:97-100,258-260) for the k=0 plane.  Frames are written by the device
+ * into a pinned host ring; the consumer takes them in order.
+ * phb_record_next: blocks until the next frame is complete (or timeout_ms elapses ->
+ * returns 2 with *tt = -1); on success *frame points at ring memory holding, for each
+ * recorded component in the order ux, uy, uz, a (planes, Ny') float64 array, and *tt is
+ * the step index the frame belongs to.  The slot stays valid until phb_record_release. */
+int phb_record_next(phb_ctx *ctx, const double **frame, int64_t *tt, int32_t timeout_ms);
+int phb_record_release(phb_ctx *ctx);
+int phb_record_frame_doubles(phb_ctx *ctx, int64_t *n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PHB200_H */

@@ -1,0 +1,188 @@
+// fd_common.cuh -- shared device-side definitions for the sm_100a FDTD kernels.
+//
+// What is computed is the time step of phonomena/simulation/base_solver.py:245-260:
+//   update_T (:323-372), apply_T_tfbc (:402-433), update_u (:435-463), apply_u_tfbc (:488-517)
+// fused into one pass: the six stresses are on-chip intermediates, never stored.
+// Index-level semantics: SURVEY.md App. A.  Quirks that are replicated on purpose: App. B.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace phb {
+
+// ---------------------------------------------------------------------------------------
+// Arithmetic policy.
+//  EXACT: every operation is a separately rounded IEEE op in the reference's order
+//         (`C*diff/sd` left to right, true division), so fp64 results are bit-identical to
+//         NumPy's.  The *_rn intrinsics are never contracted into FMAs by nvcc.
+//  FAST : spacing arrays hold reciprocals, `scl` multiplies, the compiler may contract.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double rn_add(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double rn_sub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double rn_mul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double rn_div(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ float rn_add(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float rn_sub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float rn_mul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float rn_div(float a, float b) { return __fdiv_rn(a, b); }
+
+template <class T_, bool EXACT_>
+struct Ar {
+    using T = T_;
+    static constexpr bool EXACT = EXACT_;
+    static __device__ __forceinline__ T add(T a, T b) {
+        if constexpr (EXACT) return rn_add(a, b); else return a + b;
+    }
+    static __device__ __forceinline__ T sub(T a, T b) {
+        if constexpr (EXACT) return rn_sub(a, b); else return a - b;
+    }
+    static __device__ __forceinline__ T mul(T a, T b) {
+        if constexpr (EXACT) return rn_mul(a, b); else return a * b;
+    }
+    // "divide by a spacing": s holds the spacing (EXACT) or its reciprocal (FAST)
+    static __device__ __forceinline__ T scl(T a, T s) {
+        if constexpr (EXACT) return rn_div(a, s); else return a * s;
+    }
+};
+
+// ---------------------------------------------------------------------------------------
+// Geometry / layout.
+// Device layout of every displacement component: [local plane l][j][k] with z fastest,
+// z pitch nzp (>= nz, multiple of the vector width), local plane l = i - x0 + 1 so that
+// l = 0 and l = nxl + 1 are the ghost planes of an x-slab.  All three components use the
+// same (nx, ny, nzp) box; the entries the reference's staggered shapes do not have
+// (ux at i = nx-1, uy at j = ny-1, uz at k = nz-1, the z padding) stay zero forever.
+// ---------------------------------------------------------------------------------------
+template <class T>
+struct Geo {
+    int nx, ny, nz;       // global grid points
+    int x0, nxl;          // owned planes [x0, x0+nxl)
+    int nzp;              // z pitch in elements
+    long long ps;         // plane stride = ny * nzp
+    // per-axis spacing tables (spacing in EXACT mode, reciprocal in FAST mode), each
+    // addressable on [-1, n]: fd*[m] = x[m+1]-x[m], sd*[m] = (fd[m+1]+fd[m])/2  (grid.py:118-127)
+    const T *fdx, *fdy, *fdz, *sdx, *sdy, *sdz;
+    // first elements, used on the k = 0 plane (App. B #1)
+    T fdx0, fdy0, fdz0, sdx0, sdy0, sdz0;
+
+    __device__ __forceinline__ long long idx(int i, int j, int k) const {
+        return ((long long)(i - x0 + 1) * ny + j) * nzp + k;
+    }
+};
+
+template <class T>
+struct Fld {            // one displacement buffer (three components)
+    T *ux, *uy, *uz;
+};
+
+// Material: per-cell "stencil code" = seven table indices packed B bits each, already
+// shifted to where the stencil centred on (i,j,k) needs them (k = 0 variants included):
+//   field 0 node : C rows 0..2 at (i,j,k)            -> T1,T2,T3(i,j,k)
+//   field 1 t4   : C44 at (i, j+1, k+1 | k=0: 0)     -> T4(i,j,k)     (base_solver.py:353,421)
+//   field 2 t5   : C55 at (i+1, j, k+1 | k=0: 0)     -> T5(i,j,k)     (:360,426)
+//   field 3 t6   : C66 at (i+1, j+1, k)              -> T6(i,j,k)     (:367,431)
+//   field 4 rx   : rho at (i+1, j, k)                -> ux_new(i,j,k) (:443,497)
+//   field 5 ry   : rho at (i, j+1, k)                -> uy_new(i,j,k) (:451,505)
+//   field 6 rz   : rho at (i, j, k+1 | k=0: 0)       -> uz_new(i,j,k) (:459,513)
+// Table row (13 values): c11 c12 c13 c21 c22 c23 c31 c32 c33 c44 c55 c66 d2/rho.
+enum { F_NODE = 0, F_T4 = 1, F_T5 = 2, F_T6 = 3, F_RX = 4, F_RY = 5, F_RZ = 6 };
+enum { TAB_W = 13, TAB_C44 = 9, TAB_C55 = 10, TAB_C66 = 11, TAB_RINV = 12, MAX_MAT = 16 };
+
+template <class CodeT, int B>
+__device__ __forceinline__ int code_field(CodeT c, int f) {
+    return (int)((c >> (f * B)) & (CodeT)((1u << B) - 1u));
+}
+
+template <class T, class CodeT_, int B_>
+struct MatIdx {
+    using CodeT = CodeT_;
+    static constexpr int B = B_;
+    const CodeT *code;   // same indexing as the fields
+    const T *tab;        // nmat x TAB_W
+};
+
+// ---------------------------------------------------------------------------------------
+// Formulas on values (shared by every kernel so that all variants round identically).
+// ---------------------------------------------------------------------------------------
+// T_r = C[r][0]*dxx/sx + C[r][1]*dyy/sy + C[r][2]*dzz/sz      (base_solver.py:329-351,408-416)
+template <class A>
+__device__ __forceinline__ typename A::T normal_row(const typename A::T *c3, typename A::T dxx, typename A::T dyy,
+                                                    typename A::T dzz, typename A::T sx, typename A::T sy,
+                                                    typename A::T sz) {
+    return A::add(A::add(A::scl(A::mul(c3[0], dxx), sx), A::scl(A::mul(c3[1], dyy), sy)),
+                  A::scl(A::mul(c3[2], dzz), sz));
+}
+// T = C * (a/sa + b/sb)                                        (base_solver.py:353-372,420-433)
+template <class A>
+__device__ __forceinline__ typename A::T shear(typename A::T c, typename A::T a, typename A::T sa,
+                                               typename A::T b, typename A::T sb) {
+    return A::mul(c, A::add(A::scl(a, sa), A::scl(b, sb)));
+}
+// u_new = 2u - u_old + (d2/rho) * acc                          (base_solver.py:441-463,495-517)
+template <class A>
+__device__ __forceinline__ typename A::T advance(typename A::T u, typename A::T uo, typename A::T rinv,
+                                                 typename A::T acc) {
+    return A::add(A::sub(A::mul((typename A::T)2, u), uo), A::mul(rinv, acc));
+}
+
+// ---------------------------------------------------------------------------------------
+// Generic (global-memory) stress evaluation with the reference's write ranges: anything the
+// reference never writes is identically zero (App. A.1).  Used by the naive kernel, by the
+// stress dump (phb_get_stress) and as the specification the marching kernel is tested against.
+// ---------------------------------------------------------------------------------------
+template <class A, class M>
+struct Eval {
+    using T = typename A::T;
+    const Geo<T> &g;
+    const Fld<T> &u;
+    const M &m;
+    __device__ Eval(const Geo<T> &g_, const Fld<T> &u_, const M &m_) : g(g_), u(u_), m(m_) {}
+
+    __device__ __forceinline__ T tab(int id, int e) const { return __ldg(m.tab + id * TAB_W + e); }
+    __device__ __forceinline__ int fld(int i, int j, int k, int f) const {
+        return code_field<typename M::CodeT, M::B>(__ldg(m.code + g.idx(i, j, k)), f);
+    }
+
+    // T1, T2, T3 at node (i,j,k)
+    __device__ __forceinline__ void normal(int i, int j, int k, T &t1, T &t2, T &t3) const {
+        t1 = t2 = t3 = (T)0;
+        if (i < 1 || i > g.nx - 2 || j < 1 || j > g.ny - 2 || k < 0 || k > g.nz - 2) return;
+        const bool k0 = (k == 0);
+        const T dxx = A::sub(u.ux[g.idx(i, j, k)], u.ux[g.idx(i - 1, j, k)]);
+        const T dyy = A::sub(u.uy[g.idx(i, j, k)], u.uy[g.idx(i, j - 1, k)]);
+        const T dzz = k0 ? u.uz[g.idx(i, j, 0)] : A::sub(u.uz[g.idx(i, j, k)], u.uz[g.idx(i, j, k - 1)]);
+        const T sx = k0 ? g.sdx0 : g.sdx[i - 1];
+        const T sy = k0 ? g.sdy0 : g.sdy[j - 1];
+        const T sz = k0 ? g.sdz0 : g.sdz[k - 1];
+        const int id = fld(i, j, k, F_NODE);
+        T c[9];
+#pragma unroll
+        for (int e = 0; e < 9; ++e) c[e] = tab(id, e);
+        t1 = normal_row<A>(c + 0, dxx, dyy, dzz, sx, sy, sz);
+        t2 = normal_row<A>(c + 3, dxx, dyy, dzz, sx, sy, sz);
+        t3 = k0 ? (T)0 : normal_row<A>(c + 6, dxx, dyy, dzz, sx, sy, sz);
+    }
+    __device__ __forceinline__ T t4(int i, int j, int k) const {
+        if (i < 1 || i > g.nx - 2 || j < 0 || j > g.ny - 2 || k < 0 || k > g.nz - 2) return (T)0;
+        const bool k0 = (k == 0);
+        const T a = A::sub(u.uy[g.idx(i, j, k + 1)], u.uy[g.idx(i, j, k)]);
+        const T b = A::sub(u.uz[g.idx(i, j + 1, k)], u.uz[g.idx(i, j, k)]);
+        return shear<A>(tab(fld(i, j, k, F_T4), TAB_C44), a, k0 ? g.fdy0 : g.fdz[k], b, k0 ? g.fdz0 : g.fdy[j]);
+    }
+    __device__ __forceinline__ T t5(int i, int j, int k) const {
+        if (i < 0 || i > g.nx - 2 || j < 1 || j > g.ny - 2 || k < 0 || k > g.nz - 2) return (T)0;
+        const bool k0 = (k == 0);
+        const T a = A::sub(u.ux[g.idx(i, j, k + 1)], u.ux[g.idx(i, j, k)]);
+        const T b = A::sub(u.uz[g.idx(i + 1, j, k)], u.uz[g.idx(i, j, k)]);
+        return shear<A>(tab(fld(i, j, k, F_T5), TAB_C55), a, k0 ? g.fdx0 : g.fdz[k], b, k0 ? g.fdz0 : g.fdx[i]);
+    }
+    __device__ __forceinline__ T t6(int i, int j, int k) const {
+        if (i < 0 || i > g.nx - 2 || j < 0 || j > g.ny - 2 || k < 0 || k > g.nz - 2) return (T)0;
+        const bool k0 = (k == 0);
+        const T a = A::sub(u.ux[g.idx(i, j + 1, k)], u.ux[g.idx(i, j, k)]);
+        const T b = A::sub(u.uy[g.idx(i + 1, j, k)], u.uy[g.idx(i, j, k)]);
+        return shear<A>(tab(fld(i, j, k, F_T6), TAB_C66), a, k0 ? g.fdx0 : g.fdy[j], b, k0 ? g.fdz0 : g.fdx[i]);
+    }
+};
+
+}  // namespace phb

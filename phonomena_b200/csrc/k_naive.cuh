@@ -1,0 +1,113 @@
+// k_naive.cuh -- straightforward fused step kernel: one thread per cell, every stress the
+// cell needs is re-evaluated from global memory (L1/L2 absorb the re-reads).  It is the
+// on-device specification: small, obviously equal to SURVEY App. A, validated bit-for-bit
+// against the oracle; the marching kernel (k_march.cuh) is validated against both.
+#pragma once
+#include "fd_common.cuh"
+
+namespace phb {
+
+template <class T>
+struct StepArgs {
+    Geo<T> g;
+    Fld<T> cur, old, nw;
+    const T *line_save;   // pre-source uz(0, j, 0) of `cur` (App. B #9), or nullptr
+    int i_begin, i_end;   // global planes to update: [i_begin, i_end)
+};
+
+// u_new for one cell from generic stress evaluations.  Writes only entries the reference's
+// physics writes (App. A.3/A.4 ranges) plus the i = 0 copy that keeps `u_new == u` where
+// nothing is ever written (App. B #9).
+template <class A, class M>
+__device__ __forceinline__ void naive_cell(const StepArgs<typename A::T> &p, const M &m, int i, int j, int k) {
+    using T = typename A::T;
+    const Geo<T> &g = p.g;
+    Eval<A, M> ev(g, p.cur, m);
+    const bool k0 = (k == 0);
+    const long long c = g.idx(i, j, k);
+    if (k > g.nz - 2) return;   // k = nz-1: ABC face (ux, uy) / non-existent (uz)
+
+    // ---- ux: 0<=i<=nx-2, 1<=j<=ny-2 -------------------------------------------------------
+    if (i <= g.nx - 2 && j >= 1 && j <= g.ny - 2) {
+        T a1, a2, a3, b1, b2, b3;
+        ev.normal(i + 1, j, k, a1, a2, a3);
+        ev.normal(i, j, k, b1, b2, b3);
+        const T dA = A::sub(a1, b1);
+        const T dB = A::sub(ev.t6(i, j, k), ev.t6(i, j - 1, k));
+        const T dC = k0 ? ev.t5(i, j, 0) : A::sub(ev.t5(i, j, k), ev.t5(i, j, k - 1));
+        const T acc = A::add(A::add(A::scl(dA, k0 ? g.fdx0 : g.fdx[i]), A::scl(dB, k0 ? g.sdy0 : g.sdy[j - 1])),
+                             A::scl(dC, k0 ? g.sdz0 : g.sdz[k - 1]));
+        const T rinv = ev.tab(ev.fld(i, j, k, F_RX), TAB_RINV);
+        p.nw.ux[c] = advance<A>(p.cur.ux[c], p.old.ux[c], rinv, acc);
+    }
+    // ---- uy: 1<=i<=nx-2, 0<=j<=ny-2 -------------------------------------------------------
+    if (i >= 1 && i <= g.nx - 2 && j <= g.ny - 2) {
+        T a1, a2, a3, b1, b2, b3;
+        ev.normal(i, j + 1, k, a1, a2, a3);
+        ev.normal(i, j, k, b1, b2, b3);
+        const T dA = A::sub(ev.t6(i, j, k), ev.t6(i - 1, j, k));
+        const T dB = A::sub(a2, b2);
+        const T dC = k0 ? ev.t4(i, j, 0) : A::sub(ev.t4(i, j, k), ev.t4(i, j, k - 1));
+        const T acc = A::add(A::add(A::scl(dA, k0 ? g.sdx0 : g.sdx[i - 1]), A::scl(dB, k0 ? g.fdy0 : g.fdy[j])),
+                             A::scl(dC, k0 ? g.sdz0 : g.sdz[k - 1]));
+        const T rinv = ev.tab(ev.fld(i, j, k, F_RY), TAB_RINV);
+        p.nw.uy[c] = advance<A>(p.cur.uy[c], p.old.uy[c], rinv, acc);
+    }
+    // ---- uz: 1<=i<=nx-2, 1<=j<=ny-2 -------------------------------------------------------
+    if (i >= 1 && i <= g.nx - 2 && j >= 1 && j <= g.ny - 2) {
+        T a1, a2, a3, b1, b2, b3;
+        ev.normal(i, j, k + 1, a1, a2, a3);
+        ev.normal(i, j, k, b1, b2, b3);
+        const T dA = A::sub(ev.t5(i, j, k), ev.t5(i - 1, j, k));
+        const T dB = A::sub(ev.t4(i, j, k), ev.t4(i, j - 1, k));
+        const T sA = A::scl(dA, k0 ? g.sdx0 : g.sdx[i - 1]);
+        const T sB = A::scl(dB, k0 ? g.sdy0 : g.sdy[j - 1]);
+        T acc;
+        if (k0) {
+            // "+ T3[..,1] - T3[..,0]/fdz[0]" with T3[..,0] == 0 (base_solver.py:516, App. B #3)
+            acc = A::sub(A::add(A::add(sA, sB), a3), A::scl(b3, g.fdz0));
+        } else {
+            acc = A::add(A::add(sA, sB), A::scl(A::sub(a3, b3), g.fdz[k]));
+        }
+        const T rinv = ev.tab(ev.fld(i, j, k, F_RZ), TAB_RINV);
+        p.nw.uz[c] = advance<A>(p.cur.uz[c], p.old.uz[c], rinv, acc);
+    }
+    // ---- i = 0: uy, uz are never written by the physics; keep u_new == u (App. B #9) ------
+    if (i == 0) {
+        if (j <= g.ny - 2) p.nw.uy[c] = p.cur.uy[c];
+        p.nw.uz[c] = (k0 && p.line_save) ? p.line_save[j] : p.cur.uz[c];
+    }
+}
+
+// grid: x -> k tiles, y -> j tiles, z -> plane (i_begin + blockIdx.z)
+template <class A, class M>
+__global__ void __launch_bounds__(256) k_step_naive(StepArgs<typename A::T> p, M m) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    const int i = p.i_begin + blockIdx.z;
+    if (k >= p.g.nz || j >= p.g.ny || i >= p.i_end) return;
+    naive_cell<A, M>(p, m, i, j, k);
+}
+
+// Stress dump in the reference's array shapes (double), for phb_get_stress.
+// nT1 planes etc. are the owned plane counts; out arrays are plane-major like the host arrays.
+template <class A, class M>
+__global__ void k_stress_dump(Geo<typename A::T> g, Fld<typename A::T> u, M m, int i_begin, int i_end,
+                              double *T1, double *T2, double *T3, double *T4, double *T5, double *T6) {
+    using T = typename A::T;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    const int i = i_begin + blockIdx.z;
+    if (k >= g.nz || j >= g.ny || i >= i_end) return;
+    Eval<A, M> ev(g, u, m);
+    const long long li = i - i_begin;
+    T t1, t2, t3;
+    ev.normal(i, j, k, t1, t2, t3);
+    const long long n = (li * g.ny + j) * g.nz + k;
+    T1[n] = (double)t1; T2[n] = (double)t2; T3[n] = (double)t3;
+    if (j < g.ny - 1 && k < g.nz - 1) T4[(li * (g.ny - 1) + j) * (g.nz - 1) + k] = (double)ev.t4(i, j, k);
+    if (i < g.nx - 1 && k < g.nz - 1) T5[(li * g.ny + j) * (g.nz - 1) + k] = (double)ev.t5(i, j, k);
+    if (i < g.nx - 1 && j < g.ny - 1) T6[(li * (g.ny - 1) + j) * g.nz + k] = (double)ev.t6(i, j, k);
+}
+
+}  // namespace phb

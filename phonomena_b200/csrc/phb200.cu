@@ -1,0 +1,838 @@
+// phb200.cu -- host side of libphb200.so: C ABI (include/phb200.h), device memory, step
+// orchestration, NCCL halo exchange, pinned-ring surface recorder.  sm_100a only.
+#include "../../include/phb200.h"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <atomic>
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "fd_common.cuh"
+#include "k_boundary.cuh"
+#include "k_march.cuh"
+#include "k_naive.cuh"
+
+using namespace phb;
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(const char *fmt, ...) {
+    char b[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(b, sizeof b, fmt, ap);
+    va_end(ap);
+    g_err = b;
+    return 1;
+}
+#define CU(x)                                                                                       \
+    do {                                                                                            \
+        cudaError_t e_ = (x);                                                                       \
+        if (e_ != cudaSuccess) return fail("%s:%d %s -> %s", __FILE__, __LINE__, #x, cudaGetErrorString(e_)); \
+    } while (0)
+#define OK(x)                 \
+    do {                      \
+        int r_ = (x);         \
+        if (r_) return r_;    \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------
+// NCCL through dlopen: the library has no link-time NCCL dependency (single-GPU use needs
+// none); in a torch process the already-loaded libnccl.so.2 is picked up by SONAME.
+// ------------------------------------------------------------------------------------------
+struct Nccl {
+    void *h = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+static Nccl g_nccl;
+static std::mutex g_nccl_mu;
+static int nccl_load() {
+    std::lock_guard<std::mutex> lk(g_nccl_mu);
+    if (g_nccl.h) return 0;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    void *h = nullptr;
+    for (const char *n : names) {
+        h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    if (!h) return fail("cannot dlopen libnccl.so.2: %s", dlerror());
+#define SYM(f)                                                                  \
+    *(void **)(&g_nccl.f) = dlsym(h, "nccl" #f);                                \
+    if (!g_nccl.f) return fail("libnccl: missing symbol nccl" #f);
+    SYM(GetUniqueId) SYM(CommInitRank) SYM(CommDestroy) SYM(Send) SYM(Recv) SYM(GroupStart) SYM(GroupEnd)
+    SYM(GetErrorString)
+#undef SYM
+    g_nccl.h = h;
+    return 0;
+}
+#define NC(x)                                                                                          \
+    do {                                                                                               \
+        ncclResult_t r_ = (x);                                                                         \
+        if (r_ != ncclSuccess) return fail("%s:%d %s -> %s", __FILE__, __LINE__, #x, g_nccl.GetErrorString(r_)); \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------
+struct IEngine {
+    virtual ~IEngine() {}
+    virtual int set_spacing(const double *, const double *, const double *, const double *, const double *,
+                            const double *) = 0;
+    virtual int set_table(int, const double *, const double *) = 0;
+    virtual int build_codes() = 0;
+    virtual int set_abc(const double *) = 0;
+    virtual int xfer(bool to_dev, int which, double *ux, double *uy, double *uz) = 0;
+    virtual int stress(int which, double *T[6]) = 0;
+    virtual int step() = 0;
+    virtual const char *kernel_name() = 0;
+};
+
+struct phb_ctx {
+    phb_cfg cfg;
+    int nzp = 0;
+    long long ps = 0;          // plane stride (elements)
+    size_t esz = 0;            // sizeof(T)
+    int device = 0;
+    cudaStream_t st = nullptr, cst = nullptr;
+    cudaEvent_t ev_edge = nullptr, ev_comm = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+    void *buf[3][3] = {};      // [buffer][component], each (nxl+2) planes
+    int cur = 0;               // buffer holding u; old = (cur+2)%3, new = (cur+1)%3
+    void *sp[6] = {};          // fdx fdy fdz sdx sdy sdz (padded, +1 offset applied at use)
+    double sp0[6] = {};        // first elements (spacing)
+    bool have_spacing = false;
+    void *tab = nullptr;
+    int nmat = 0;
+    uint8_t *ids = nullptr;    // raw ids, planes [ids_ib, ids_ie)
+    int ids_ib = 0, ids_ie = 0;
+    void *code = nullptr;
+    int code_bits = 0;         // 1, 2 or 4
+    void *line_save = nullptr;
+    double *w = nullptr;
+    long long nw = 0;
+    double abc[8] = {};
+    bool have_abc = false;
+    long long tt = 0;
+    std::atomic<long long> launches{0};
+    long long dev_bytes = 0;
+    // comm
+    ncclComm_t comm = nullptr;
+    int rank = 0, nranks = 1;
+    // recorder
+    double *ring = nullptr;    // pinned host, mapped
+    double *ring_dev = nullptr;
+    long long frame_doubles = 0;
+    int slots = 0;
+    std::vector<cudaEvent_t> slot_ev;
+    std::vector<long long> slot_tt;
+    std::atomic<long long> produced{0}, consumed{0}, released{0};
+    IEngine *eng = nullptr;
+    std::mutex mu;
+};
+
+static int dmalloc(phb_ctx *c, void **p, size_t bytes, bool zero = true) {
+    cudaError_t e = cudaMalloc(p, bytes ? bytes : 1);
+    if (e != cudaSuccess)
+        return fail("cudaMalloc(%zu bytes) failed: %s (allocated so far: %lld bytes)", bytes, cudaGetErrorString(e),
+                    c->dev_bytes);
+    c->dev_bytes += (long long)bytes;
+    if (zero) CU(cudaMemsetAsync(*p, 0, bytes ? bytes : 1, c->st));
+    return 0;
+}
+
+static inline dim3 grid3(int nx, int ny, int nz, dim3 b) {
+    return dim3((nx + b.x - 1) / b.x, (ny + b.y - 1) / b.y, (nz + b.z - 1) / b.z);
+}
+static inline dim3 block_for(int nfast) {
+    int bx = 32;
+    while (bx < nfast && bx < 128) bx <<= 1;
+    return dim3(bx, 256 / bx, 1);
+}
+
+// ------------------------------------------------------------------------------------------
+// typed engine
+// ------------------------------------------------------------------------------------------
+template <class T>
+struct Engine : IEngine {
+    phb_ctx *c;
+    explicit Engine(phb_ctx *c_) : c(c_) {}
+
+    Geo<T> geo() const {
+        Geo<T> g;
+        g.nx = c->cfg.nx; g.ny = c->cfg.ny; g.nz = c->cfg.nz;
+        g.x0 = c->cfg.x0; g.nxl = c->cfg.nxl;
+        g.nzp = c->nzp; g.ps = c->ps;
+        g.fdx = (const T *)c->sp[0] + 1; g.fdy = (const T *)c->sp[1] + 1; g.fdz = (const T *)c->sp[2] + 1;
+        g.sdx = (const T *)c->sp[3] + 1; g.sdy = (const T *)c->sp[4] + 1; g.sdz = (const T *)c->sp[5] + 1;
+        const bool ex = c->cfg.arith == PHB_EXACT;
+        auto f = [&](double s) { return (T)(ex ? s : 1.0 / s); };
+        g.fdx0 = f(c->sp0[0]); g.fdy0 = f(c->sp0[1]); g.fdz0 = f(c->sp0[2]);
+        g.sdx0 = f(c->sp0[3]); g.sdy0 = f(c->sp0[4]); g.sdz0 = f(c->sp0[5]);
+        return g;
+    }
+    Fld<T> fld(int b) const { return Fld<T>{(T *)c->buf[b][0], (T *)c->buf[b][1], (T *)c->buf[b][2]}; }
+    int b_cur() const { return c->cur; }
+    int b_old() const { return (c->cur + 2) % 3; }
+    int b_new() const { return (c->cur + 1) % 3; }
+
+    int set_spacing(const double *fdx, const double *fdy, const double *fdz, const double *sdx, const double *sdy,
+                    const double *sdz) override {
+        const double *src[6] = {fdx, fdy, fdz, sdx, sdy, sdz};
+        const int n[3] = {c->cfg.nx, c->cfg.ny, c->cfg.nz};
+        const bool ex = c->cfg.arith == PHB_EXACT;
+        for (int a = 0; a < 6; ++a) {
+            const int ax = a % 3, len = (a < 3) ? n[ax] - 1 : n[ax] - 2;
+            std::vector<T> h(n[ax] + 2, (T)1);
+            for (int m = 0; m < len; ++m) {
+                if (!(src[a][m] > 0)) return fail("spacing array %d has a non-positive entry at %d", a, m);
+                h[m + 1] = (T)(ex ? src[a][m] : 1.0 / src[a][m]);
+            }
+            c->sp0[a] = src[a][0];
+            if (!c->sp[a]) OK(dmalloc(c, &c->sp[a], h.size() * sizeof(T)));
+            CU(cudaMemcpyAsync(c->sp[a], h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, c->st));
+            CU(cudaStreamSynchronize(c->st));
+        }
+        c->have_spacing = true;
+        return 0;
+    }
+
+    int set_table(int nmat, const double *c12, const double *rho) override {
+        std::vector<T> h((size_t)nmat * TAB_W);
+        for (int m = 0; m < nmat; ++m) {
+            for (int e = 0; e < 12; ++e) h[(size_t)m * TAB_W + e] = (T)c12[m * 12 + e];
+            // (dt**2 / P) is evaluated first in the reference (base_solver.py:443), in float64
+            h[(size_t)m * TAB_W + TAB_RINV] = (T)(c->cfg.d2 / rho[m]);
+        }
+        if (c->tab) { cudaFree(c->tab); c->tab = nullptr; }
+        OK(dmalloc(c, &c->tab, h.size() * sizeof(T)));
+        CU(cudaMemcpyAsync(c->tab, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, c->st));
+        CU(cudaStreamSynchronize(c->st));
+        c->nmat = nmat;
+        return 0;
+    }
+
+    int build_codes() override {
+        if (!c->ids) return fail("material ids not set");
+        const int bits = c->nmat <= 2 ? 1 : (c->nmat <= 4 ? 2 : 4);
+        const size_t cb = bits == 1 ? 1 : (bits == 2 ? 2 : 4);
+        if (c->code && c->code_bits != bits) { cudaFree(c->code); c->code = nullptr; }
+        if (!c->code) OK(dmalloc(c, &c->code, (size_t)(c->cfg.nxl + 2) * c->ps * cb));
+        c->code_bits = bits;
+        dim3 b = block_for(c->nzp), g = grid3(c->nzp, c->cfg.ny, c->cfg.nxl + 2, b);
+#define BC(CT, B)                                                                                               \
+    k_build_codes<CT, B><<<g, b, 0, c->st>>>(c->ids, c->ids_ib, c->ids_ie, (CT *)c->code, c->cfg.nx, c->cfg.ny, \
+                                             c->cfg.nz, c->nzp, c->cfg.x0, c->cfg.nxl)
+        if (bits == 1) BC(uint8_t, 1); else if (bits == 2) BC(uint16_t, 2); else BC(uint32_t, 4);
+#undef BC
+        c->launches++;
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(c->st));
+        return 0;
+    }
+
+    int set_abc(const double *k) override {
+        memcpy(c->abc, k, sizeof c->abc);
+        c->have_abc = true;
+        return 0;
+    }
+
+    // planes of component comp owned by this slab, in host arrays
+    int owned_planes(int comp) const {
+        const int hi = (comp == 0) ? c->cfg.nx - 1 : c->cfg.nx;
+        int e = c->cfg.x0 + c->cfg.nxl;
+        if (e > hi) e = hi;
+        return e - c->cfg.x0 > 0 ? e - c->cfg.x0 : 0;
+    }
+
+    int xfer(bool to_dev, int which, double *ux, double *uy, double *uz) override {
+        const int b = which == PHB_CUR ? b_cur() : b_old();
+        double *h[3] = {ux, uy, uz};
+        for (int comp = 0; comp < 3; ++comp) {
+            if (!h[comp]) continue;
+            const int np = owned_planes(comp);
+            const int ey = c->cfg.ny - (comp == 1), ez = c->cfg.nz - (comp == 2);
+            const size_t bytes = (size_t)np * ey * ez * sizeof(double);
+            if (!bytes) continue;
+            double *tmp = nullptr;
+            CU(cudaMalloc(&tmp, bytes));
+            dim3 bl = block_for(ez), g = grid3(ez, ey, np, bl);
+            if (to_dev) {
+                CU(cudaMemcpyAsync(tmp, h[comp], bytes, cudaMemcpyHostToDevice, c->st));
+                k_scatter<T><<<g, bl, 0, c->st>>>(tmp, (T *)c->buf[b][comp], np, ey, ez, 1, c->cfg.ny, c->nzp);
+            } else {
+                k_gather<T><<<g, bl, 0, c->st>>>((const T *)c->buf[b][comp], tmp, np, ey, ez, 1, c->cfg.ny, c->nzp);
+                CU(cudaMemcpyAsync(h[comp], tmp, bytes, cudaMemcpyDeviceToHost, c->st));
+            }
+            c->launches++;
+            cudaError_t e = cudaStreamSynchronize(c->st);
+            cudaFree(tmp);
+            CU(e);
+            CU(cudaGetLastError());
+        }
+        return 0;
+    }
+
+    template <class F>
+    int dispatch(F &&f) {
+        // f.template operator()<A, M>(mat)
+        const bool ex = c->cfg.arith == PHB_EXACT;
+#define DO(EX, CT, B)                                                 \
+    {                                                                 \
+        MatIdx<T, CT, B> m{(const CT *)c->code, (const T *)c->tab};   \
+        return f.template operator()<Ar<T, EX>, MatIdx<T, CT, B>>(m); \
+    }
+        if (c->code_bits == 1) { if (ex) DO(true, uint8_t, 1) else DO(false, uint8_t, 1) }
+        if (c->code_bits == 2) { if (ex) DO(true, uint16_t, 2) else DO(false, uint16_t, 2) }
+        if (c->code_bits == 4) { if (ex) DO(true, uint32_t, 4) else DO(false, uint32_t, 4) }
+#undef DO
+        return fail("material codes not built");
+    }
+
+    int stress(int which, double *Th[6]) override {
+        if (!c->have_spacing || !c->code) return fail("spacing/material not set");
+        const int b = which == PHB_CUR ? b_cur() : b_old();
+        const int nx = c->cfg.nx, ny = c->cfg.ny, nz = c->cfg.nz;
+        const int n = c->cfg.nxl, n5 = owned_planes(0);
+        const size_t cnt[6] = {(size_t)n * ny * nz, (size_t)n * ny * nz, (size_t)n * ny * nz,
+                               (size_t)n * (ny - 1) * (nz - 1), (size_t)n5 * ny * (nz - 1),
+                               (size_t)n5 * (ny - 1) * nz};
+        double *d[6] = {};
+        for (int q = 0; q < 6; ++q) {
+            CU(cudaMalloc(&d[q], (cnt[q] ? cnt[q] : 1) * sizeof(double)));
+            CU(cudaMemsetAsync(d[q], 0, cnt[q] * sizeof(double), c->st));
+        }
+        Geo<T> g = geo();
+        Fld<T> u = fld(b);
+        dim3 bl = block_for(nz), gr = grid3(nz, ny, n, bl);
+        const int ib = c->cfg.x0, ie = c->cfg.x0 + n;
+        (void)nx;
+        auto run = [&]<class A, class M>(M m) -> int {
+            k_stress_dump<A, M><<<gr, bl, 0, c->st>>>(g, u, m, ib, ie, d[0], d[1], d[2], d[3], d[4], d[5]);
+            return 0;
+        };
+        int r = dispatch(run);
+        c->launches++;
+        cudaError_t e = cudaGetLastError();
+        for (int q = 0; q < 6 && !r && e == cudaSuccess; ++q)
+            if (Th[q]) e = cudaMemcpyAsync(Th[q], d[q], cnt[q] * sizeof(double), cudaMemcpyDeviceToHost, c->st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->st);
+        for (int q = 0; q < 6; ++q) cudaFree(d[q]);
+        if (r) return r;
+        CU(e);
+        return 0;
+    }
+
+    // ---- one time step -----------------------------------------------------------------------
+    int physics(int ib, int ie) {
+        if (ie <= ib) return 0;
+        StepArgs<T> p;
+        p.g = geo();
+        p.cur = fld(b_cur()); p.old = fld(b_old()); p.nw = fld(b_new());
+        p.line_save = (c->w && c->cfg.x0 == 0) ? (const T *)c->line_save : nullptr;
+        p.i_begin = ib; p.i_end = ie;
+        const bool march = use_march();
+        if (c->cfg.kernel == PHB_KERNEL_MARCH && !march)
+            return fail("kernel=march requested but the marching kernel does not support this grid");
+        auto run = [&]<class A, class M>(M m) -> int {
+            if (march) {
+                c->launches += launch_march<A, M>(p, m, c->st);
+            } else {
+                dim3 bl = block_for(c->cfg.nz), gr = grid3(c->cfg.nz, c->cfg.ny, ie - ib, bl);
+                k_step_naive<A, M><<<gr, bl, 0, c->st>>>(p, m);
+                c->launches++;
+            }
+            return 0;
+        };
+        OK(dispatch(run));
+        CU(cudaGetLastError());
+        return 0;
+    }
+    bool use_march() const {
+        if (c->cfg.kernel == PHB_KERNEL_NAIVE) return false;
+        return march_supported<T>(c->cfg.nx, c->cfg.ny, c->cfg.nz, c->nzp);
+    }
+    const char *kernel_name() override { return use_march() ? march_name<T>() : "naive"; }
+
+    AbcArgs<T> abc_args(int ib, int ie) {
+        AbcArgs<T> a;
+        a.g = geo(); a.cur = fld(b_cur()); a.nw = fld(b_new());
+        a.clx = (T)c->abc[0]; a.ctx = (T)c->abc[1]; a.cly0 = (T)c->abc[2]; a.cty0 = (T)c->abc[3];
+        a.cly1 = (T)c->abc[4]; a.cty1 = (T)c->abc[5]; a.clz = (T)c->abc[6]; a.ctz = (T)c->abc[7];
+        a.i_begin = ib; a.i_end = ie;
+        return a;
+    }
+    int abc_x() {
+        AbcArgs<T> a = abc_args(0, 0);
+        dim3 bl = block_for(c->cfg.nz), gr = grid3(c->cfg.nz, c->cfg.ny, 1, bl);
+        if (c->cfg.arith == PHB_EXACT) k_abc_x<Ar<T, true>><<<gr, bl, 0, c->st>>>(a);
+        else k_abc_x<Ar<T, false>><<<gr, bl, 0, c->st>>>(a);
+        c->launches++;
+        CU(cudaGetLastError());
+        return 0;
+    }
+    int abc_yz(int ib, int ie) {
+        if (ie <= ib) return 0;
+        AbcArgs<T> a = abc_args(ib, ie);
+        {
+            dim3 bl = block_for(c->cfg.nz), gr = grid3(c->cfg.nz, ie - ib, 1, bl);
+            gr.z = 2;
+            if (c->cfg.arith == PHB_EXACT) k_abc_y<Ar<T, true>><<<gr, bl, 0, c->st>>>(a);
+            else k_abc_y<Ar<T, false>><<<gr, bl, 0, c->st>>>(a);
+        }
+        {
+            dim3 bl(32, 8, 1), gr = grid3(c->cfg.ny, ie - ib, 1, bl);
+            if (c->cfg.arith == PHB_EXACT) k_abc_z<Ar<T, true>><<<gr, bl, 0, c->st>>>(a);
+            else k_abc_z<Ar<T, false>><<<gr, bl, 0, c->st>>>(a);
+        }
+        c->launches += 2;
+        CU(cudaGetLastError());
+        return 0;
+    }
+
+    int exchange() {
+        // send new[x0] to the left neighbour (its right ghost), new[x0+nxl-1] to the right
+        // neighbour (its left ghost); receive the mirror images.  3 components per direction.
+        const ncclDataType_t dt = sizeof(T) == 8 ? ncclDouble : ncclFloat;
+        const size_t n = (size_t)c->ps;
+        const int bn = b_new();
+        NC(g_nccl.GroupStart());
+        for (int comp = 0; comp < 3; ++comp) {
+            T *base = (T *)c->buf[bn][comp];
+            if (c->rank > 0) {
+                NC(g_nccl.Send(base + 1 * c->ps, n, dt, c->rank - 1, c->comm, c->cst));
+                NC(g_nccl.Recv(base + 0 * c->ps, n, dt, c->rank - 1, c->comm, c->cst));
+            }
+            if (c->rank < c->nranks - 1) {
+                NC(g_nccl.Send(base + (long long)c->cfg.nxl * c->ps, n, dt, c->rank + 1, c->comm, c->cst));
+                NC(g_nccl.Recv(base + (long long)(c->cfg.nxl + 1) * c->ps, n, dt, c->rank + 1, c->comm, c->cst));
+            }
+        }
+        NC(g_nccl.GroupEnd());
+        c->launches++;
+        return 0;
+    }
+
+    int step() override {
+        const int x0 = c->cfg.x0, xe = c->cfg.x0 + c->cfg.nxl;
+        const bool last = (xe == c->cfg.nx);
+        if (c->w && x0 == 0) {
+            if (c->tt >= c->nw) return fail("source table has %lld entries, step %lld requested", c->nw, c->tt);
+            k_source<T><<<(c->cfg.ny + 127) / 128, 128, 0, c->st>>>(geo(), (T *)c->buf[b_cur()][2], (T *)c->line_save,
+                                                                   c->w, c->tt);
+            c->launches++;
+        }
+        if (c->comm && c->nranks > 1) {
+            // edge planes first so that the exchange overlaps the interior update
+            const bool hasL = c->rank > 0, hasR = c->rank < c->nranks - 1;
+            int ib = x0, ie = xe;
+            if (hasL) { OK(physics(x0, x0 + 1)); OK(abc_yz(x0, x0 + 1)); ib = x0 + 1; }
+            if (hasR) { OK(physics(xe - 1, xe)); OK(abc_yz(xe - 1, xe)); ie = xe - 1; }
+            CU(cudaEventRecord(c->ev_edge, c->st));
+            CU(cudaStreamWaitEvent(c->cst, c->ev_edge, 0));
+            OK(exchange());
+            CU(cudaEventRecord(c->ev_comm, c->cst));
+            OK(physics(ib, ie));
+            if (last) OK(abc_x());
+            OK(abc_yz(ib, ie));
+            CU(cudaStreamWaitEvent(c->st, c->ev_comm, 0));
+        } else {
+            OK(physics(x0, xe));
+            if (last) OK(abc_x());
+            OK(abc_yz(x0, xe));
+        }
+        c->cur = b_new();   // rotate: old <- cur, cur <- new
+        c->tt++;
+        return 0;
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// recorder
+// ------------------------------------------------------------------------------------------
+static int record_frame(phb_ctx *c) {
+    // flow control: wait for a free slot
+    while (c->produced.load() - c->released.load() >= c->slots) std::this_thread::sleep_for(std::chrono::microseconds(50));
+    const long long f = c->produced.load();
+    const int s = (int)(f % c->slots);
+    double *slot = c->ring_dev + (long long)s * c->frame_doubles;
+    const int npx = std::max(0, std::min(c->cfg.x0 + c->cfg.nxl, c->cfg.nx - 1) - c->cfg.x0), npyz = c->cfg.nxl;
+    dim3 bl(128, 1, 1), gr((c->cfg.ny + 127) / 128, c->cfg.nxl, 1);
+    if (c->cfg.dtype == PHB_F64) {
+        auto *e = static_cast<Engine<double> *>(c->eng);
+        k_record<double><<<gr, bl, 0, c->st>>>(e->geo(), e->fld(c->cur), c->cfg.record_mask, slot, npx, npyz);
+    } else {
+        auto *e = static_cast<Engine<float> *>(c->eng);
+        k_record<float><<<gr, bl, 0, c->st>>>(e->geo(), e->fld(c->cur), c->cfg.record_mask, slot, npx, npyz);
+    }
+    c->launches++;
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(c->slot_ev[s], c->st));
+    c->slot_tt[s] = c->tt - 1;
+    c->produced.fetch_add(1);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+int phb_version(void) { return PHB_VERSION; }
+const char *phb_last_error(void) { return g_err.c_str(); }
+
+int phb_device_count(int *n) {
+    cudaError_t e = cudaGetDeviceCount(n);
+    if (e != cudaSuccess) { *n = 0; return fail("cudaGetDeviceCount: %s", cudaGetErrorString(e)); }
+    return 0;
+}
+
+int phb_create(const phb_cfg *cfg, phb_ctx **out) {
+    if (!cfg || !out) return fail("null argument");
+    *out = nullptr;
+    if (cfg->nx < 4 || cfg->ny < 4 || cfg->nz < 4) return fail("grid must be at least 4 points per axis (got %d x %d x %d)", cfg->nx, cfg->ny, cfg->nz);
+    if (cfg->x0 < 0 || cfg->nxl < 1 || cfg->x0 + cfg->nxl > cfg->nx) return fail("bad slab [%d, %d) of %d", cfg->x0, cfg->x0 + cfg->nxl, cfg->nx);
+    if (cfg->dtype != PHB_F32 && cfg->dtype != PHB_F64) return fail("bad dtype %d", cfg->dtype);
+    if (cfg->arith != PHB_FAST && cfg->arith != PHB_EXACT) return fail("bad arith %d", cfg->arith);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail("no CUDA device available (%s); libphb200 has no CPU fallback", e == cudaSuccess ? "count = 0" : cudaGetErrorString(e));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail("device %d out of range (%d devices)", cfg->device, ndev);
+    CU(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10) return fail("device %d is sm_%d%d; this library is built for sm_100a (B200) only", cfg->device, prop.major, prop.minor);
+
+    phb_ctx *c = new phb_ctx();
+    c->cfg = *cfg;
+    if (c->cfg.record_every < 1) c->cfg.record_every = 1;
+    c->device = cfg->device;
+    c->esz = cfg->dtype == PHB_F64 ? 8 : 4;
+    c->nzp = (cfg->nz + 31) / 32 * 32;
+    c->ps = (long long)cfg->ny * c->nzp;
+    auto cleanup = [&](int r) { phb_destroy(c); return r; };
+    if (cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess) return cleanup(fail("stream create failed"));
+    if (cudaStreamCreateWithFlags(&c->cst, cudaStreamNonBlocking) != cudaSuccess) return cleanup(fail("stream create failed"));
+    cudaEventCreateWithFlags(&c->ev_edge, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_comm, cudaEventDisableTiming);
+    cudaEventCreate(&c->ev_t0);
+    cudaEventCreate(&c->ev_t1);
+    const size_t fb = (size_t)(cfg->nxl + 2) * c->ps * c->esz;
+    for (int b = 0; b < 3; ++b)
+        for (int q = 0; q < 3; ++q)
+            if (dmalloc(c, &c->buf[b][q], fb)) return cleanup(1);
+    if (dmalloc(c, &c->line_save, (size_t)cfg->ny * c->esz)) return cleanup(1);
+    if (cfg->dtype == PHB_F64) c->eng = new Engine<double>(c); else c->eng = new Engine<float>(c);
+    // recorder ring
+    if (cfg->record_mask) {
+        const int npx = std::max(0, std::min(cfg->x0 + cfg->nxl, cfg->nx - 1) - cfg->x0);
+        long long fd = 0;
+        if (cfg->record_mask & PHB_REC_UX) fd += (long long)npx * cfg->ny;
+        if (cfg->record_mask & PHB_REC_UY) fd += (long long)cfg->nxl * (cfg->ny - 1);
+        if (cfg->record_mask & PHB_REC_UZ) fd += (long long)cfg->nxl * cfg->ny;
+        c->frame_doubles = fd;
+        c->slots = cfg->ring_slots > 0 ? cfg->ring_slots : 16;
+        if (cudaHostAlloc((void **)&c->ring, (size_t)c->slots * fd * sizeof(double), cudaHostAllocMapped) != cudaSuccess)
+            return cleanup(fail("cudaHostAlloc of the %d-slot recorder ring failed", c->slots));
+        if (cudaHostGetDevicePointer((void **)&c->ring_dev, c->ring, 0) != cudaSuccess) return cleanup(fail("cudaHostGetDevicePointer failed"));
+        c->slot_ev.resize(c->slots);
+        c->slot_tt.assign(c->slots, -1);
+        for (auto &ev : c->slot_ev) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    }
+    if (cudaStreamSynchronize(c->st) != cudaSuccess) return cleanup(fail("device init failed: %s", cudaGetErrorString(cudaGetLastError())));
+    *out = c;
+    return 0;
+}
+
+int phb_destroy(phb_ctx *c) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    if (c->st) cudaStreamSynchronize(c->st);
+    if (c->cst) cudaStreamSynchronize(c->cst);
+    if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    for (int b = 0; b < 3; ++b)
+        for (int q = 0; q < 3; ++q) cudaFree(c->buf[b][q]);
+    for (int a = 0; a < 6; ++a) cudaFree(c->sp[a]);
+    cudaFree(c->tab); cudaFree(c->ids); cudaFree(c->code); cudaFree(c->line_save); cudaFree(c->w);
+    if (c->ring) cudaFreeHost(c->ring);
+    for (auto &ev : c->slot_ev) cudaEventDestroy(ev);
+    if (c->ev_edge) cudaEventDestroy(c->ev_edge);
+    if (c->ev_comm) cudaEventDestroy(c->ev_comm);
+    if (c->ev_t0) cudaEventDestroy(c->ev_t0);
+    if (c->ev_t1) cudaEventDestroy(c->ev_t1);
+    if (c->st) cudaStreamDestroy(c->st);
+    if (c->cst) cudaStreamDestroy(c->cst);
+    delete c->eng;
+    delete c;
+    return 0;
+}
+
+#define ENTER(c)                              \
+    if (!(c)) return fail("null context");    \
+    std::lock_guard<std::mutex> lk_((c)->mu); \
+    CU(cudaSetDevice((c)->device));
+
+int phb_set_spacing(phb_ctx *c, const double *fdx, const double *fdy, const double *fdz, const double *sdx,
+                    const double *sdy, const double *sdz) {
+    ENTER(c);
+    if (!fdx || !fdy || !fdz || !sdx || !sdy || !sdz) return fail("null spacing array");
+    return c->eng->set_spacing(fdx, fdy, fdz, sdx, sdy, sdz);
+}
+
+int phb_set_material_table(phb_ctx *c, int32_t nmat, const double *c12, const double *rho) {
+    ENTER(c);
+    if (nmat < 1 || nmat > MAX_MAT) return fail("nmat must be 1..%d (got %d)", MAX_MAT, nmat);
+    for (int m = 0; m < nmat; ++m)
+        if (!(rho[m] > 0)) return fail("density of material %d is not positive", m);
+    OK(c->eng->set_table(nmat, c12, rho));
+    if (c->ids) OK(c->eng->build_codes());
+    return 0;
+}
+
+static int ids_planes(const phb_ctx *c, int *ib, int *ie) {
+    *ib = c->cfg.x0;
+    *ie = std::min(c->cfg.x0 + c->cfg.nxl + 1, c->cfg.nx);
+    return *ie - *ib;
+}
+
+int phb_set_material_ids(phb_ctx *c, const uint8_t *ids, int64_t nplanes) {
+    ENTER(c);
+    int ib, ie;
+    const int np = ids_planes(c, &ib, &ie);
+    if (nplanes != np) return fail("expected %d id planes [%d, %d), got %lld", np, ib, ie, (long long)nplanes);
+    const size_t bytes = (size_t)np * c->cfg.ny * c->cfg.nz;
+    if (!c->ids) OK(dmalloc(c, (void **)&c->ids, bytes, false));
+    c->ids_ib = ib; c->ids_ie = ie;
+    CU(cudaMemcpyAsync(c->ids, ids, bytes, cudaMemcpyHostToDevice, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    if (c->nmat) OK(c->eng->build_codes());
+    return 0;
+}
+
+int phb_gen_material_ids(phb_ctx *c, const float *tg, int32_t n, const double *x, const double *y, const double *z) {
+    ENTER(c);
+    if (n < 0 || (n && !tg) || !x || !y || !z) return fail("bad arguments");
+    const int nx = c->cfg.nx, ny = c->cfg.ny, nz = c->cfg.nz;
+    int ib, ie;
+    const int np = ids_planes(c, &ib, &ie);
+    // z profile per inclusion, with the re-binding of `z` to the index array (grid.py:173)
+    std::vector<double> zc(z, z + nz);
+    std::vector<std::vector<int>> prof(n);
+    for (int t = 0; t < n; ++t) {
+        std::vector<int> idx;
+        for (int m = 0; m < (int)zc.size(); ++m)
+            if (zc[m] <= (double)tg[4 * t + 2]) idx.push_back(m);
+        prof[t] = idx;
+        zc.assign(idx.begin(), idx.end());
+    }
+    std::vector<std::vector<int>> groups;
+    std::vector<int> group(n, 0);
+    for (int t = 0; t < n; ++t) {
+        int gi = -1;
+        for (size_t q = 0; q < groups.size(); ++q)
+            if (groups[q] == prof[t]) { gi = (int)q; break; }
+        if (gi < 0) {
+            if (groups.size() == 32) return fail("more than 32 distinct inclusion depth profiles; upload ids with phb_set_material_ids instead");
+            groups.push_back(prof[t]);
+            gi = (int)groups.size() - 1;
+        }
+        group[t] = gi;
+    }
+    std::vector<unsigned> zbits(nz, 0u);
+    for (size_t q = 0; q < groups.size(); ++q)
+        for (int m : groups[q])
+            if (m >= 0 && m < nz) zbits[m] |= 1u << q;
+    const size_t bytes = (size_t)np * ny * nz;
+    if (!c->ids) OK(dmalloc(c, (void **)&c->ids, bytes, false));
+    c->ids_ib = ib; c->ids_ie = ie;
+    double *dx = nullptr, *dy = nullptr;
+    float *dt = nullptr;
+    int *dg = nullptr;
+    unsigned *dcol = nullptr, *dz = nullptr;
+    CU(cudaMalloc(&dx, nx * sizeof(double)));
+    CU(cudaMalloc(&dy, ny * sizeof(double)));
+    CU(cudaMalloc(&dt, (n ? n : 1) * 4 * sizeof(float)));
+    CU(cudaMalloc(&dg, (n ? n : 1) * sizeof(int)));
+    CU(cudaMalloc(&dcol, (size_t)np * ny * sizeof(unsigned)));
+    CU(cudaMalloc(&dz, nz * sizeof(unsigned)));
+    CU(cudaMemcpyAsync(dx, x, nx * sizeof(double), cudaMemcpyHostToDevice, c->st));
+    CU(cudaMemcpyAsync(dy, y, ny * sizeof(double), cudaMemcpyHostToDevice, c->st));
+    if (n) {
+        CU(cudaMemcpyAsync(dt, tg, (size_t)n * 4 * sizeof(float), cudaMemcpyHostToDevice, c->st));
+        CU(cudaMemcpyAsync(dg, group.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, c->st));
+    }
+    CU(cudaMemcpyAsync(dz, zbits.data(), nz * sizeof(unsigned), cudaMemcpyHostToDevice, c->st));
+    k_incl_columns<<<dim3((ny + 127) / 128, np, 1), 128, 0, c->st>>>(dx, dy, ib, ie, ny, dt, dg, n, dcol);
+    dim3 bl = block_for(nz);
+    k_incl_fill<<<grid3(nz, ny, np, bl), bl, 0, c->st>>>(dcol, dz, c->ids, np, ny, nz);
+    c->launches += 2;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->st);
+    cudaFree(dx); cudaFree(dy); cudaFree(dt); cudaFree(dg); cudaFree(dcol); cudaFree(dz);
+    CU(e);
+    if (c->nmat) OK(c->eng->build_codes());
+    return 0;
+}
+
+int phb_get_material_ids(phb_ctx *c, uint8_t *ids) {
+    ENTER(c);
+    if (!c->ids) return fail("material ids not set");
+    CU(cudaMemcpyAsync(ids, c->ids, (size_t)c->cfg.nxl * c->cfg.ny * c->cfg.nz, cudaMemcpyDeviceToHost, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    return 0;
+}
+
+int phb_set_abc(phb_ctx *c, const double coef[8]) {
+    ENTER(c);
+    return c->eng->set_abc(coef);
+}
+
+int phb_set_source_table(phb_ctx *c, const double *w, int64_t n) {
+    ENTER(c);
+    if (c->w) { cudaFree(c->w); c->w = nullptr; c->nw = 0; }
+    if (!w || n <= 0) return 0;
+    OK(dmalloc(c, (void **)&c->w, (size_t)n * sizeof(double), false));
+    CU(cudaMemcpyAsync(c->w, w, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    c->nw = n;
+    return 0;
+}
+
+int phb_set_fields(phb_ctx *c, int32_t which, const double *ux, const double *uy, const double *uz) {
+    ENTER(c);
+    if (which != PHB_CUR && which != PHB_OLD) return fail("bad buffer selector %d", which);
+    return c->eng->xfer(true, which, (double *)ux, (double *)uy, (double *)uz);
+}
+int phb_get_fields(phb_ctx *c, int32_t which, double *ux, double *uy, double *uz) {
+    ENTER(c);
+    if (which != PHB_CUR && which != PHB_OLD) return fail("bad buffer selector %d", which);
+    return c->eng->xfer(false, which, ux, uy, uz);
+}
+int phb_get_stress(phb_ctx *c, int32_t which, double *T1, double *T2, double *T3, double *T4, double *T5,
+                   double *T6) {
+    ENTER(c);
+    double *T[6] = {T1, T2, T3, T4, T5, T6};
+    return c->eng->stress(which, T);
+}
+
+static int run_locked(phb_ctx *c, int64_t nsteps) {
+    if (!c->have_spacing) return fail("phb_set_spacing not called");
+    if (!c->code) return fail("material not set (table + ids)");
+    if (!c->have_abc) return fail("phb_set_abc not called");
+    if (c->nranks > 1 && !c->comm) return fail("slab context without communicator: call phb_comm_init");
+    for (int64_t s = 0; s < nsteps; ++s) {
+        OK(c->eng->step());
+        if (c->cfg.record_mask && (c->tt % c->cfg.record_every) == 0) OK(record_frame(c));
+    }
+    return 0;
+}
+
+int phb_run(phb_ctx *c, int64_t nsteps) {
+    ENTER(c);
+    return run_locked(c, nsteps);
+}
+int phb_sync(phb_ctx *c) {
+    ENTER(c);
+    CU(cudaStreamSynchronize(c->st));
+    CU(cudaStreamSynchronize(c->cst));
+    return 0;
+}
+int phb_run_timed(phb_ctx *c, int64_t nsteps, float *ms) {
+    ENTER(c);
+    CU(cudaStreamSynchronize(c->st));
+    CU(cudaStreamSynchronize(c->cst));
+    CU(cudaEventRecord(c->ev_t0, c->st));
+    OK(run_locked(c, nsteps));
+    CU(cudaEventRecord(c->ev_t1, c->st));
+    CU(cudaEventSynchronize(c->ev_t1));
+    CU(cudaStreamSynchronize(c->cst));
+    CU(cudaEventElapsedTime(ms, c->ev_t0, c->ev_t1));
+    return 0;
+}
+int phb_steps_done(phb_ctx *c, int64_t *tt) {
+    if (!c) return fail("null context");
+    *tt = c->tt;
+    return 0;
+}
+int phb_launch_count(phb_ctx *c, int64_t *n) {
+    if (!c) return fail("null context");
+    *n = c->launches.load();
+    return 0;
+}
+int phb_info(phb_ctx *c, char *name, int32_t len, int64_t *bytes) {
+    if (!c) return fail("null context");
+    if (name && len > 0) snprintf(name, len, "%s", c->eng->kernel_name());
+    if (bytes) *bytes = c->dev_bytes;
+    return 0;
+}
+
+int phb_comm_unique_id(char id[128]) {
+    OK(nccl_load());
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    ncclUniqueId u;
+    NC(g_nccl.GetUniqueId(&u));
+    memcpy(id, &u, 128);
+    return 0;
+}
+int phb_comm_init(phb_ctx *c, const char id[128], int32_t rank, int32_t nranks) {
+    ENTER(c);
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail("bad rank %d of %d", rank, nranks);
+    c->rank = rank; c->nranks = nranks;
+    if (nranks == 1) return 0;
+    if (c->cfg.nxl < 4) return fail("a slab needs at least 4 planes (got %d)", c->cfg.nxl);
+    OK(nccl_load());
+    ncclUniqueId u;
+    memcpy(&u, id, 128);
+    NC(g_nccl.CommInitRank(&c->comm, nranks, u, rank));
+    return 0;
+}
+
+int phb_record_frame_doubles(phb_ctx *c, int64_t *n) {
+    if (!c) return fail("null context");
+    *n = c->frame_doubles;
+    return 0;
+}
+int phb_record_next(phb_ctx *c, const double **frame, int64_t *tt, int32_t timeout_ms) {
+    if (!c || !c->ring) return fail("recording not enabled");
+    if (c->consumed.load() != c->released.load()) return fail("previous frame not released");
+    auto t0 = std::chrono::steady_clock::now();
+    while (c->produced.load() <= c->consumed.load()) {
+        if (std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - t0).count() >= timeout_ms) {
+            *tt = -1; *frame = nullptr;
+            g_err = "timeout";
+            return 2;   // timeout, not an error
+        }
+        std::this_thread::sleep_for(std::chrono::microseconds(100));
+    }
+    const int s = (int)(c->consumed.load() % c->slots);
+    cudaSetDevice(c->device);
+    CU(cudaEventSynchronize(c->slot_ev[s]));
+    *frame = c->ring + (long long)s * c->frame_doubles;
+    *tt = c->slot_tt[s];
+    c->consumed.fetch_add(1);
+    return 0;
+}
+int phb_record_release(phb_ctx *c) {
+    if (!c || !c->ring) return fail("recording not enabled");
+    if (c->released.load() < c->consumed.load()) c->released.fetch_add(1);
+    return 0;
+}
+
+}  // extern "C"
