@@ -10,6 +10,7 @@
 #include <chrono>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -102,6 +103,7 @@ struct IEngine {
     virtual int xfer(bool to_dev, int which, double *ux, double *uy, double *uz) = 0;
     virtual int stress(int which, double *T[6]) = 0;
     virtual int step() = 0;
+    virtual int make_maps() = 0;
     virtual const char *kernel_name() = 0;
 };
 
@@ -143,6 +145,10 @@ struct phb_ctx {
     std::vector<cudaEvent_t> slot_ev;
     std::vector<long long> slot_tt;
     std::atomic<long long> produced{0}, consumed{0}, released{0};
+    // marching kernel: TMA descriptors per [buffer][component], tile plan
+    CUtensorMap maps[3][3];
+    bool maps_ok = false;
+    int mR = 16, mNST = 3, mChunks = 0;
     IEngine *eng = nullptr;
     std::mutex mu;
 };
@@ -352,7 +358,12 @@ struct Engine : IEngine {
             return fail("kernel=march requested but the marching kernel does not support this grid");
         auto run = [&]<class A, class M>(M m) -> int {
             if (march) {
-                c->launches += launch_march<A, M>(p, m, c->st);
+                const CUtensorMap *mp = c->maps[b_cur()];
+                const int ch = plan_chunks(ie - ib);
+                if (c->mR == 16 && c->mNST == 3) c->launches += launch_march_cfg<A, M, 16, 3>(p, m, mp, c->nmat, ch, c->st);
+                else if (c->mR == 16 && c->mNST == 4) c->launches += launch_march_cfg<A, M, 16, 4>(p, m, mp, c->nmat, ch, c->st);
+                else if (c->mR == 8 && c->mNST == 4) c->launches += launch_march_cfg<A, M, 8, 4>(p, m, mp, c->nmat, ch, c->st);
+                else return fail("no marching-kernel instantiation for R=%d NST=%d", c->mR, c->mNST);
             } else {
                 dim3 bl = block_for(c->cfg.nz), gr = grid3(c->cfg.nz, c->cfg.ny, ie - ib, bl);
                 k_step_naive<A, M><<<gr, bl, 0, c->st>>>(p, m);
@@ -366,7 +377,37 @@ struct Engine : IEngine {
     }
     bool use_march() const {
         if (c->cfg.kernel == PHB_KERNEL_NAIVE) return false;
-        return march_supported<T>(c->cfg.nx, c->cfg.ny, c->cfg.nz, c->nzp);
+        return c->maps_ok;
+    }
+    // x-chunks per launch: fill whole waves of (148 SMs x resident blocks) with the (y,z) tiles
+    int plan_chunks(int np) const {
+        if (c->mChunks > 0) return c->mChunks;
+        const int V = VecOf<T>::V, TZ = 32 * V, TY = c->mR - 2;
+        const long long tiles = (long long)((c->nzp + TZ - 1) / TZ) * ((c->cfg.ny + TY - 1) / TY);
+        const long long slots = 148LL * (c->mR <= 8 ? 2 : 1);
+        int best = 1;
+        double best_eff = 0;
+        for (int ch = 1; ch <= 16 && ch * 8 <= np; ++ch) {
+            const long long blocks = tiles * ch, waves = (blocks + slots - 1) / slots;
+            const double eff = (double)blocks / (double)(waves * slots) * (1.0 - 1.5 * ch / (double)np);
+            if (eff > best_eff + 1e-9) { best_eff = eff; best = ch; }
+        }
+        return best;
+    }
+    int make_maps() override {
+        c->maps_ok = false;
+        if (c->cfg.kernel == PHB_KERNEL_NAIVE) return 0;
+        for (int b = 0; b < 3; ++b)
+            for (int q = 0; q < 3; ++q) {
+                bool ok = (c->mR == 16) ? make_field_map<T, 16>(&c->maps[b][q], c->buf[b][q], c->nzp, c->cfg.ny, c->cfg.nxl + 2)
+                                        : make_field_map<T, 8>(&c->maps[b][q], c->buf[b][q], c->nzp, c->cfg.ny, c->cfg.nxl + 2);
+                if (!ok) {
+                    if (c->cfg.kernel == PHB_KERNEL_MARCH) return fail("cuTensorMapEncodeTiled failed for buffer %d component %d", b, q);
+                    return 0;
+                }
+            }
+        c->maps_ok = true;
+        return 0;
     }
     const char *kernel_name() override { return use_march() ? march_name<T>() : "naive"; }
 
@@ -540,6 +581,11 @@ int phb_create(const phb_cfg *cfg, phb_ctx **out) {
             if (dmalloc(c, &c->buf[b][q], fb)) return cleanup(1);
     if (dmalloc(c, &c->line_save, (size_t)cfg->ny * c->esz)) return cleanup(1);
     if (cfg->dtype == PHB_F64) c->eng = new Engine<double>(c); else c->eng = new Engine<float>(c);
+    if (const char *e = getenv("PHB_MARCH_R")) c->mR = atoi(e);
+    if (const char *e = getenv("PHB_MARCH_NST")) c->mNST = atoi(e);
+    if (const char *e = getenv("PHB_MARCH_CHUNKS")) c->mChunks = atoi(e);
+    if (c->mR != 8 && c->mR != 16) return cleanup(fail("PHB_MARCH_R must be 8 or 16"));
+    if (c->eng->make_maps()) return cleanup(1);
     // recorder ring
     if (cfg->record_mask) {
         const int npx = std::max(0, std::min(cfg->x0 + cfg->nxl, cfg->nx - 1) - cfg->x0);
