@@ -75,31 +75,37 @@ struct Fld {            // one displacement buffer (three components)
     T *ux, *uy, *uz;
 };
 
-// Material: per-cell "stencil code" = seven table indices packed B bits each, already
-// shifted to where the stencil centred on (i,j,k) needs them (k = 0 variants included):
-//   field 0 node : C rows 0..2 at (i,j,k)            -> T1,T2,T3(i,j,k)
-//   field 1 t4   : C44 at (i, j+1, k+1 | k=0: 0)     -> T4(i,j,k)     (base_solver.py:353,421)
-//   field 2 t5   : C55 at (i+1, j, k+1 | k=0: 0)     -> T5(i,j,k)     (:360,426)
-//   field 3 t6   : C66 at (i+1, j+1, k)              -> T6(i,j,k)     (:367,431)
-//   field 4 rx   : rho at (i+1, j, k)                -> ux_new(i,j,k) (:443,497)
-//   field 5 ry   : rho at (i, j+1, k)                -> uy_new(i,j,k) (:451,505)
-//   field 6 rz   : rho at (i, j, k+1 | k=0: 0)       -> uz_new(i,j,k) (:459,513)
-// Table row (13 values): c11 c12 c13 c21 c22 c23 c31 c32 c33 c44 c55 c66 d2/rho.
-enum { F_NODE = 0, F_T4 = 1, F_T5 = 2, F_T6 = 3, F_RX = 4, F_RY = 5, F_RZ = 6 };
-enum { TAB_W = 13, TAB_C44 = 9, TAB_C55 = 10, TAB_C66 = 11, TAB_RINV = 12, MAX_MAT = 16 };
+// Material: one byte per cell = index of a "stencil class".  A class is the 7-tuple of
+// material ids the stencil centred on (i,j,k) reads, already shifted to where each update
+// needs them (k = 0 variants included) and already VOIDed where the reference never writes
+// the corresponding stress / displacement (App. A.1 "never written => identically 0"), so the
+// range masks of the reference's slices are data, not code:
+//   node : C rows 0..2 at (i,j,k)            -> T1,T2,T3(i,j,k)   (row 3 zeroed on k = 0: T3 = 0, :418)
+//   t4   : C44 at (i, j+1, k+1 | k=0: 0)     -> T4(i,j,k)         (base_solver.py:353,421)
+//   t5   : C55 at (i+1, j, k+1 | k=0: 0)     -> T5(i,j,k)         (:360,426)
+//   t6   : C66 at (i+1, j+1, k)              -> T6(i,j,k)         (:367,431)
+//   rx   : rho at (i+1, j, k)                -> ux_new(i,j,k)     (:443,497)
+//   ry   : rho at (i, j+1, k)                -> uy_new(i,j,k)     (:451,505)
+//   rz   : rho at (i, j, k+1 | k=0: 0)       -> uz_new(i,j,k)     (:459,513)
+// Class-table row (CLS_W values): c11 c12 c13 c21 c22 c23 c31 c32 c33 c44 c55 c66 rx ry rz pad,
+// with rX = dt^2/rho; a VOID entry is 0.  Classes are the distinct tuples present in the
+// grid, sorted by key (deterministic numbering), at most 256.
+enum { CLS_W = 16, CLS_C44 = 9, CLS_C55 = 10, CLS_C66 = 11, CLS_RX = 12, CLS_RY = 13, CLS_RZ = 14, MAX_MAT = 15,
+       MAT_VOID = 15, MAX_CLS = 256 };
 
-template <class CodeT, int B>
-__device__ __forceinline__ int code_field(CodeT c, int f) {
-    return (int)((c >> (f * B)) & (CodeT)((1u << B) - 1u));
-}
-
-template <class T, class CodeT_, int B_>
-struct MatIdx {
-    using CodeT = CodeT_;
-    static constexpr int B = B_;
-    const CodeT *code;   // same indexing as the fields
-    const T *tab;        // nmat x TAB_W
+template <class T>
+struct MatCls {
+    const uint8_t *code;   // same indexing as the fields
+    const T *tab;          // ncls x CLS_W
+    int ncls;
 };
+
+// 4 bits per id, 7 ids, bit 28 = "k == 0" (T3 forced to zero)
+__host__ __device__ inline uint32_t cls_key(const int id[7], bool k0) {
+    uint32_t key = k0 ? (1u << 28) : 0u;
+    for (int f = 0; f < 7; ++f) key |= (uint32_t)(id[f] & 15) << (4 * f);
+    return key;
+}
 
 // ---------------------------------------------------------------------------------------
 // Formulas on values (shared by every kernel so that all variants round identically).
@@ -138,9 +144,9 @@ struct Eval {
     const M &m;
     __device__ Eval(const Geo<T> &g_, const Fld<T> &u_, const M &m_) : g(g_), u(u_), m(m_) {}
 
-    __device__ __forceinline__ T tab(int id, int e) const { return __ldg(m.tab + id * TAB_W + e); }
-    __device__ __forceinline__ int fld(int i, int j, int k, int f) const {
-        return code_field<typename M::CodeT, M::B>(__ldg(m.code + g.idx(i, j, k)), f);
+    // coefficient e of the class of cell (i,j,k)
+    __device__ __forceinline__ T coef(int i, int j, int k, int e) const {
+        return __ldg(m.tab + (int)__ldg(m.code + g.idx(i, j, k)) * CLS_W + e);
     }
 
     // T1, T2, T3 at node (i,j,k)
@@ -154,10 +160,9 @@ struct Eval {
         const T sx = k0 ? g.sdx0 : g.sdx[i - 1];
         const T sy = k0 ? g.sdy0 : g.sdy[j - 1];
         const T sz = k0 ? g.sdz0 : g.sdz[k - 1];
-        const int id = fld(i, j, k, F_NODE);
         T c[9];
 #pragma unroll
-        for (int e = 0; e < 9; ++e) c[e] = tab(id, e);
+        for (int e = 0; e < 9; ++e) c[e] = coef(i, j, k, e);
         t1 = normal_row<A>(c + 0, dxx, dyy, dzz, sx, sy, sz);
         t2 = normal_row<A>(c + 3, dxx, dyy, dzz, sx, sy, sz);
         t3 = k0 ? (T)0 : normal_row<A>(c + 6, dxx, dyy, dzz, sx, sy, sz);
@@ -167,21 +172,21 @@ struct Eval {
         const bool k0 = (k == 0);
         const T a = A::sub(u.uy[g.idx(i, j, k + 1)], u.uy[g.idx(i, j, k)]);
         const T b = A::sub(u.uz[g.idx(i, j + 1, k)], u.uz[g.idx(i, j, k)]);
-        return shear<A>(tab(fld(i, j, k, F_T4), TAB_C44), a, k0 ? g.fdy0 : g.fdz[k], b, k0 ? g.fdz0 : g.fdy[j]);
+        return shear<A>(coef(i, j, k, CLS_C44), a, k0 ? g.fdy0 : g.fdz[k], b, k0 ? g.fdz0 : g.fdy[j]);
     }
     __device__ __forceinline__ T t5(int i, int j, int k) const {
         if (i < 0 || i > g.nx - 2 || j < 1 || j > g.ny - 2 || k < 0 || k > g.nz - 2) return (T)0;
         const bool k0 = (k == 0);
         const T a = A::sub(u.ux[g.idx(i, j, k + 1)], u.ux[g.idx(i, j, k)]);
         const T b = A::sub(u.uz[g.idx(i + 1, j, k)], u.uz[g.idx(i, j, k)]);
-        return shear<A>(tab(fld(i, j, k, F_T5), TAB_C55), a, k0 ? g.fdx0 : g.fdz[k], b, k0 ? g.fdz0 : g.fdx[i]);
+        return shear<A>(coef(i, j, k, CLS_C55), a, k0 ? g.fdx0 : g.fdz[k], b, k0 ? g.fdz0 : g.fdx[i]);
     }
     __device__ __forceinline__ T t6(int i, int j, int k) const {
         if (i < 0 || i > g.nx - 2 || j < 0 || j > g.ny - 2 || k < 0 || k > g.nz - 2) return (T)0;
         const bool k0 = (k == 0);
         const T a = A::sub(u.ux[g.idx(i, j + 1, k)], u.ux[g.idx(i, j, k)]);
         const T b = A::sub(u.uy[g.idx(i + 1, j, k)], u.uy[g.idx(i, j, k)]);
-        return shear<A>(tab(fld(i, j, k, F_T6), TAB_C66), a, k0 ? g.fdx0 : g.fdy[j], b, k0 ? g.fdz0 : g.fdx[i]);
+        return shear<A>(coef(i, j, k, CLS_C66), a, k0 ? g.fdx0 : g.fdy[j], b, k0 ? g.fdz0 : g.fdx[i]);
     }
 };
 

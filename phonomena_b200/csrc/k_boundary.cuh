@@ -128,34 +128,73 @@ __global__ void k_gather(const T *src, double *dst, int np, int ey, int ez, int 
 }
 
 // ---------------------------------------------------------------------------------------
-// Material stencil codes from the raw id box.  ids: planes [ib, ie) of the global grid,
-// unpadded (ny, nz).  One code per cell of every local plane (ghosts included); indices are
-// clamped -- a clamped lookup only ever feeds a stress the range masks zero out.
+// Stencil classes from the raw id box (see fd_common.cuh "Material").  ids: planes [ib, ie) of
+// the global grid, unpadded (ny, nz).  A field whose stress / displacement the reference never
+// writes at this cell gets MAT_VOID (App. A.1 ranges); clamped lookups only ever feed VOIDed
+// fields.  Pass 1 inserts every cell's key into a small open-addressing set; the host sorts the
+// distinct keys; pass 2 writes each cell's index in the sorted list.
 // ---------------------------------------------------------------------------------------
-template <class CodeT, int B>
-__global__ void k_build_codes(const uint8_t *ids, int ib, int ie, CodeT *code, int nx, int ny, int nz, int nzp,
-                              int x0, int nxl) {
+struct ClsGeo {
+    const uint8_t *ids;
+    int ib, ie;          // id planes available
+    int nx, ny, nz, nzp, x0, nxl;
+};
+__device__ __forceinline__ uint32_t cell_key(const ClsGeo &q, int i, int j, int k) {
+    int f[7];
+    if (i < 0 || i >= q.nx || k >= q.nz) {
+        for (int e = 0; e < 7; ++e) f[e] = MAT_VOID;
+        return cls_key(f, false);
+    }
+    auto id = [&](int ii, int jj, int kk) -> int {
+        ii = min(max(ii, q.ib), q.ie - 1);
+        jj = min(max(jj, 0), q.ny - 1);
+        kk = min(max(kk, 0), q.nz - 1);
+        return q.ids[((long long)(ii - q.ib) * q.ny + jj) * q.nz + kk];
+    };
+    const bool k0 = (k == 0);
+    const int kz = k0 ? 0 : k + 1;                     // the k = 0 plane reads its own z level (App. A.2/A.4)
+    const bool vk = (k <= q.nz - 2);
+    const bool xi = (i >= 1 && i <= q.nx - 2), xs = (i <= q.nx - 2);      // i >= 0 here
+    const bool yi = (j >= 1 && j <= q.ny - 2), ys = (j <= q.ny - 2);      // j >= 0 always
+    f[0] = (xi && yi && vk) ? id(i, j, k) : MAT_VOID;              // T1..T3
+    f[1] = (xi && ys && vk) ? id(i, j + 1, kz) : MAT_VOID;         // T4
+    f[2] = (xs && yi && vk) ? id(i + 1, j, kz) : MAT_VOID;         // T5
+    f[3] = (xs && ys && vk) ? id(i + 1, j + 1, k) : MAT_VOID;      // T6
+    f[4] = (xs && yi && vk) ? id(i + 1, j, k) : MAT_VOID;          // ux_new
+    f[5] = (xi && ys && vk) ? id(i, j + 1, k) : MAT_VOID;          // uy_new
+    f[6] = (xi && yi && vk) ? id(i, j, kz) : MAT_VOID;             // uz_new
+    return cls_key(f, k0 && f[0] != MAT_VOID);
+}
+enum { CLS_SLOTS = 4096, CLS_EMPTY = 0xFFFFFFFFu };
+__global__ void k_cls_collect(ClsGeo q, uint32_t *slots, int *overflow) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y * blockDim.y + threadIdx.y;
     const int l = blockIdx.z;                    // local plane 0 .. nxl+1
-    if (k >= nzp || j >= ny || l >= nxl + 2) return;
-    const int i = x0 - 1 + l;
-    auto id = [&](int ii, int jj, int kk) -> unsigned {
-        ii = min(max(ii, ib), ie - 1);
-        jj = min(max(jj, 0), ny - 1);
-        kk = min(max(kk, 0), nz - 1);
-        return ids[((long long)(ii - ib) * ny + jj) * nz + kk];
-    };
-    const int kz = (k == 0) ? 0 : k + 1;         // the k = 0 plane reads its own z level (App. A.2/A.4)
-    unsigned c = 0;
-    c |= id(i, j, k) << (F_NODE * B);
-    c |= id(i, j + 1, kz) << (F_T4 * B);
-    c |= id(i + 1, j, kz) << (F_T5 * B);
-    c |= id(i + 1, j + 1, k) << (F_T6 * B);
-    c |= id(i + 1, j, k) << (F_RX * B);
-    c |= id(i, j + 1, k) << (F_RY * B);
-    c |= id(i, j, kz) << (F_RZ * B);
-    code[((long long)l * ny + j) * nzp + k] = (CodeT)c;
+    if (k >= q.nzp || j >= q.ny || l >= q.nxl + 2) return;
+    const uint32_t key = cell_key(q, q.x0 - 1 + l, j, k);
+    uint32_t h = (key * 2654435761u) >> 20;      // 12 bits
+    for (int probe = 0; probe < CLS_SLOTS; ++probe, h = (h + 1) & (CLS_SLOTS - 1)) {
+        uint32_t cur = slots[h];
+        if (cur == key) return;
+        if (cur == CLS_EMPTY) {
+            cur = atomicCAS(&slots[h], CLS_EMPTY, key);
+            if (cur == CLS_EMPTY || cur == key) return;
+        }
+    }
+    *overflow = 1;
+}
+__global__ void k_cls_assign(ClsGeo q, const uint32_t *keys, int nkeys, uint8_t *code) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    const int l = blockIdx.z;
+    if (k >= q.nzp || j >= q.ny || l >= q.nxl + 2) return;
+    const uint32_t key = cell_key(q, q.x0 - 1 + l, j, k);
+    int lo = 0, hi = nkeys - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (keys[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    code[((long long)l * q.ny + j) * q.nzp + k] = (uint8_t)lo;
 }
 
 // ---------------------------------------------------------------------------------------

@@ -37,7 +37,7 @@ __device__ __forceinline__ void naive_cell(const StepArgs<typename A::T> &p, con
         const T dC = k0 ? ev.t5(i, j, 0) : A::sub(ev.t5(i, j, k), ev.t5(i, j, k - 1));
         const T acc = A::add(A::add(A::scl(dA, k0 ? g.fdx0 : g.fdx[i]), A::scl(dB, k0 ? g.sdy0 : g.sdy[j - 1])),
                              A::scl(dC, k0 ? g.sdz0 : g.sdz[k - 1]));
-        const T rinv = ev.tab(ev.fld(i, j, k, F_RX), TAB_RINV);
+        const T rinv = ev.coef(i, j, k, CLS_RX);
         p.nw.ux[c] = advance<A>(p.cur.ux[c], p.old.ux[c], rinv, acc);
     }
     // ---- uy: 1<=i<=nx-2, 0<=j<=ny-2 -------------------------------------------------------
@@ -50,7 +50,7 @@ __device__ __forceinline__ void naive_cell(const StepArgs<typename A::T> &p, con
         const T dC = k0 ? ev.t4(i, j, 0) : A::sub(ev.t4(i, j, k), ev.t4(i, j, k - 1));
         const T acc = A::add(A::add(A::scl(dA, k0 ? g.sdx0 : g.sdx[i - 1]), A::scl(dB, k0 ? g.fdy0 : g.fdy[j])),
                              A::scl(dC, k0 ? g.sdz0 : g.sdz[k - 1]));
-        const T rinv = ev.tab(ev.fld(i, j, k, F_RY), TAB_RINV);
+        const T rinv = ev.coef(i, j, k, CLS_RY);
         p.nw.uy[c] = advance<A>(p.cur.uy[c], p.old.uy[c], rinv, acc);
     }
     // ---- uz: 1<=i<=nx-2, 1<=j<=ny-2 -------------------------------------------------------
@@ -69,7 +69,7 @@ __device__ __forceinline__ void naive_cell(const StepArgs<typename A::T> &p, con
         } else {
             acc = A::add(A::add(sA, sB), A::scl(A::sub(a3, b3), g.fdz[k]));
         }
-        const T rinv = ev.tab(ev.fld(i, j, k, F_RZ), TAB_RINV);
+        const T rinv = ev.coef(i, j, k, CLS_RZ);
         p.nw.uz[c] = advance<A>(p.cur.uz[c], p.old.uz[c], rinv, acc);
     }
     // ---- i = 0: uy, uz are never written by the physics; keep u_new == u (App. B #9) ------

@@ -6,6 +6,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <cstdarg>
@@ -120,12 +121,13 @@ struct phb_ctx {
     void *sp[6] = {};          // fdx fdy fdz sdx sdy sdz (padded, +1 offset applied at use)
     double sp0[6] = {};        // first elements (spacing)
     bool have_spacing = false;
-    void *tab = nullptr;
+    std::vector<double> mat_c12, mat_rho;   // host copy of the material table
     int nmat = 0;
     uint8_t *ids = nullptr;    // raw ids, planes [ids_ib, ids_ie)
     int ids_ib = 0, ids_ie = 0;
-    void *code = nullptr;
-    int code_bits = 0;         // 1, 2 or 4
+    uint8_t *code = nullptr;   // stencil class per cell, (nxl+2) planes, padded layout
+    void *tab = nullptr;       // class table, ncls x CLS_W
+    int ncls = 0;
     void *line_save = nullptr;
     double *w = nullptr;
     long long nw = 0;
@@ -220,36 +222,71 @@ struct Engine : IEngine {
     }
 
     int set_table(int nmat, const double *c12, const double *rho) override {
-        std::vector<T> h((size_t)nmat * TAB_W);
-        for (int m = 0; m < nmat; ++m) {
-            for (int e = 0; e < 12; ++e) h[(size_t)m * TAB_W + e] = (T)c12[m * 12 + e];
-            // (dt**2 / P) is evaluated first in the reference (base_solver.py:443), in float64
-            h[(size_t)m * TAB_W + TAB_RINV] = (T)(c->cfg.d2 / rho[m]);
-        }
-        if (c->tab) { cudaFree(c->tab); c->tab = nullptr; }
-        OK(dmalloc(c, &c->tab, h.size() * sizeof(T)));
-        CU(cudaMemcpyAsync(c->tab, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, c->st));
-        CU(cudaStreamSynchronize(c->st));
+        c->mat_c12.assign(c12, c12 + (size_t)nmat * 12);
+        c->mat_rho.assign(rho, rho + nmat);
         c->nmat = nmat;
         return 0;
     }
 
+    // stencil classes: distinct (shifted, range-masked) material tuples -> 1 byte per cell + table
     int build_codes() override {
-        if (!c->ids) return fail("material ids not set");
-        const int bits = c->nmat <= 2 ? 1 : (c->nmat <= 4 ? 2 : 4);
-        const size_t cb = bits == 1 ? 1 : (bits == 2 ? 2 : 4);
-        if (c->code && c->code_bits != bits) { cudaFree(c->code); c->code = nullptr; }
-        if (!c->code) OK(dmalloc(c, &c->code, (size_t)(c->cfg.nxl + 2) * c->ps * cb));
-        c->code_bits = bits;
+        if (!c->ids || !c->nmat) return fail("material ids / table not set");
+        ClsGeo q{c->ids, c->ids_ib, c->ids_ie, c->cfg.nx, c->cfg.ny, c->cfg.nz, c->nzp, c->cfg.x0, c->cfg.nxl};
+        uint32_t *slots = nullptr, *dkeys = nullptr;
+        int *ovf = nullptr;
+        CU(cudaMalloc(&slots, CLS_SLOTS * sizeof(uint32_t)));
+        CU(cudaMalloc(&ovf, sizeof(int)));
+        CU(cudaMemsetAsync(slots, 0xFF, CLS_SLOTS * sizeof(uint32_t), c->st));
+        CU(cudaMemsetAsync(ovf, 0, sizeof(int), c->st));
         dim3 b = block_for(c->nzp), g = grid3(c->nzp, c->cfg.ny, c->cfg.nxl + 2, b);
-#define BC(CT, B)                                                                                               \
-    k_build_codes<CT, B><<<g, b, 0, c->st>>>(c->ids, c->ids_ib, c->ids_ie, (CT *)c->code, c->cfg.nx, c->cfg.ny, \
-                                             c->cfg.nz, c->nzp, c->cfg.x0, c->cfg.nxl)
-        if (bits == 1) BC(uint8_t, 1); else if (bits == 2) BC(uint16_t, 2); else BC(uint32_t, 4);
-#undef BC
-        c->launches++;
-        CU(cudaGetLastError());
-        CU(cudaStreamSynchronize(c->st));
+        k_cls_collect<<<g, b, 0, c->st>>>(q, slots, ovf);
+        std::vector<uint32_t> hs(CLS_SLOTS);
+        int hovf = 0;
+        CU(cudaMemcpyAsync(hs.data(), slots, CLS_SLOTS * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->st));
+        CU(cudaMemcpyAsync(&hovf, ovf, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+        cudaError_t e = cudaStreamSynchronize(c->st);
+        cudaFree(ovf);
+        if (e != cudaSuccess) { cudaFree(slots); CU(e); }
+        std::vector<uint32_t> keys;
+        for (uint32_t v : hs) if (v != CLS_EMPTY) keys.push_back(v);
+        std::sort(keys.begin(), keys.end());
+        cudaFree(slots);
+        if (hovf || keys.size() > MAX_CLS)
+            return fail("more than %d distinct material stencil classes (%zu found): medium too heterogeneous for the "
+                        "1-byte class code", (int)MAX_CLS, keys.size());
+        // table rows, evaluated in float64 exactly as the reference's operands
+        std::vector<T> tab(keys.size() * CLS_W, (T)0);
+        for (size_t n = 0; n < keys.size(); ++n) {
+            int f[7];
+            for (int m = 0; m < 7; ++m) f[m] = (keys[n] >> (4 * m)) & 15;
+            for (int m = 0; m < 7; ++m)
+                if (f[m] != MAT_VOID && f[m] >= c->nmat) return fail("material id %d used in the grid but the table has %d entries", f[m], c->nmat);
+            const bool k0 = (keys[n] >> 28) & 1;
+            T *row = &tab[n * CLS_W];
+            if (f[0] != MAT_VOID)
+                for (int m = 0; m < 9; ++m) row[m] = (T)c->mat_c12[(size_t)f[0] * 12 + m];
+            if (k0) row[6] = row[7] = row[8] = (T)0;                       // T3 = 0 on the free surface (:418)
+            if (f[1] != MAT_VOID) row[CLS_C44] = (T)c->mat_c12[(size_t)f[1] * 12 + 9];
+            if (f[2] != MAT_VOID) row[CLS_C55] = (T)c->mat_c12[(size_t)f[2] * 12 + 10];
+            if (f[3] != MAT_VOID) row[CLS_C66] = (T)c->mat_c12[(size_t)f[3] * 12 + 11];
+            // (dt**2 / P) is evaluated first in the reference (base_solver.py:443), in float64
+            if (f[4] != MAT_VOID) row[CLS_RX] = (T)(c->cfg.d2 / c->mat_rho[f[4]]);
+            if (f[5] != MAT_VOID) row[CLS_RY] = (T)(c->cfg.d2 / c->mat_rho[f[5]]);
+            if (f[6] != MAT_VOID) row[CLS_RZ] = (T)(c->cfg.d2 / c->mat_rho[f[6]]);
+        }
+        if (c->tab) { cudaFree(c->tab); c->tab = nullptr; }
+        OK(dmalloc(c, &c->tab, tab.size() * sizeof(T), false));
+        CU(cudaMemcpyAsync(c->tab, tab.data(), tab.size() * sizeof(T), cudaMemcpyHostToDevice, c->st));
+        c->ncls = (int)keys.size();
+        if (!c->code) OK(dmalloc(c, (void **)&c->code, (size_t)(c->cfg.nxl + 2) * c->ps));
+        CU(cudaMalloc(&dkeys, keys.size() * sizeof(uint32_t)));
+        CU(cudaMemcpyAsync(dkeys, keys.data(), keys.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->st));
+        k_cls_assign<<<g, b, 0, c->st>>>(q, dkeys, c->ncls, c->code);
+        c->launches += 2;
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->st);
+        cudaFree(dkeys);
+        CU(e);
         return 0;
     }
 
@@ -295,20 +332,12 @@ struct Engine : IEngine {
         return 0;
     }
 
+    MatCls<T> mat() const { return MatCls<T>{c->code, (const T *)c->tab, c->ncls}; }
     template <class F>
     int dispatch(F &&f) {
-        // f.template operator()<A, M>(mat)
-        const bool ex = c->cfg.arith == PHB_EXACT;
-#define DO(EX, CT, B)                                                 \
-    {                                                                 \
-        MatIdx<T, CT, B> m{(const CT *)c->code, (const T *)c->tab};   \
-        return f.template operator()<Ar<T, EX>, MatIdx<T, CT, B>>(m); \
-    }
-        if (c->code_bits == 1) { if (ex) DO(true, uint8_t, 1) else DO(false, uint8_t, 1) }
-        if (c->code_bits == 2) { if (ex) DO(true, uint16_t, 2) else DO(false, uint16_t, 2) }
-        if (c->code_bits == 4) { if (ex) DO(true, uint32_t, 4) else DO(false, uint32_t, 4) }
-#undef DO
-        return fail("material codes not built");
+        if (!c->code || !c->tab) return fail("material not set (table + ids)");
+        if (c->cfg.arith == PHB_EXACT) return f.template operator()<Ar<T, true>>();
+        return f.template operator()<Ar<T, false>>();
     }
 
     int stress(int which, double *Th[6]) override {
@@ -329,8 +358,9 @@ struct Engine : IEngine {
         dim3 bl = block_for(nz), gr = grid3(nz, ny, n, bl);
         const int ib = c->cfg.x0, ie = c->cfg.x0 + n;
         (void)nx;
-        auto run = [&]<class A, class M>(M m) -> int {
-            k_stress_dump<A, M><<<gr, bl, 0, c->st>>>(g, u, m, ib, ie, d[0], d[1], d[2], d[3], d[4], d[5]);
+        MatCls<T> m = mat();
+        auto run = [&]<class A>() -> int {
+            k_stress_dump<A, MatCls<T>><<<gr, bl, 0, c->st>>>(g, u, m, ib, ie, d[0], d[1], d[2], d[3], d[4], d[5]);
             return 0;
         };
         int r = dispatch(run);
@@ -356,17 +386,21 @@ struct Engine : IEngine {
         const bool march = use_march();
         if (c->cfg.kernel == PHB_KERNEL_MARCH && !march)
             return fail("kernel=march requested but the marching kernel does not support this grid");
-        auto run = [&]<class A, class M>(M m) -> int {
+        MatCls<T> m = mat();
+        auto run = [&]<class A>() -> int {
             if (march) {
                 const CUtensorMap *mp = c->maps[b_cur()];
                 const int ch = plan_chunks(ie - ib);
-                if (c->mR == 16 && c->mNST == 3) c->launches += launch_march_cfg<A, M, 16, 3>(p, m, mp, c->nmat, ch, c->st);
-                else if (c->mR == 16 && c->mNST == 4) c->launches += launch_march_cfg<A, M, 16, 4>(p, m, mp, c->nmat, ch, c->st);
-                else if (c->mR == 8 && c->mNST == 4) c->launches += launch_march_cfg<A, M, 8, 4>(p, m, mp, c->nmat, ch, c->st);
-                else return fail("no marching-kernel instantiation for R=%d NST=%d", c->mR, c->mNST);
+                int r = -2;
+                if (c->mR == 16 && c->mNST == 3) r = launch_march_cfg<A, 16, 3>(p, m, mp, ch, c->st);
+                else if (c->mR == 16 && c->mNST == 4) r = launch_march_cfg<A, 16, 4>(p, m, mp, ch, c->st);
+                else if (c->mR == 8 && c->mNST == 4) r = launch_march_cfg<A, 8, 4>(p, m, mp, ch, c->st);
+                if (r == -2) return fail("no marching-kernel instantiation for R=%d NST=%d", c->mR, c->mNST);
+                if (r < 0) return fail("marching kernel needs more shared memory than the device allows (%d classes)", c->ncls);
+                c->launches += r;
             } else {
                 dim3 bl = block_for(c->cfg.nz), gr = grid3(c->cfg.nz, c->cfg.ny, ie - ib, bl);
-                k_step_naive<A, M><<<gr, bl, 0, c->st>>>(p, m);
+                k_step_naive<A, MatCls<T>><<<gr, bl, 0, c->st>>>(p, m);
                 c->launches++;
             }
             return 0;
@@ -399,8 +433,7 @@ struct Engine : IEngine {
         if (c->cfg.kernel == PHB_KERNEL_NAIVE) return 0;
         for (int b = 0; b < 3; ++b)
             for (int q = 0; q < 3; ++q) {
-                bool ok = (c->mR == 16) ? make_field_map<T, 16>(&c->maps[b][q], c->buf[b][q], c->nzp, c->cfg.ny, c->cfg.nxl + 2)
-                                        : make_field_map<T, 8>(&c->maps[b][q], c->buf[b][q], c->nzp, c->cfg.ny, c->cfg.nxl + 2);
+                bool ok = make_field_map<T>(&c->maps[b][q], c->buf[b][q], c->nzp, c->cfg.ny, c->cfg.nxl + 2, c->mR);
                 if (!ok) {
                     if (c->cfg.kernel == PHB_KERNEL_MARCH) return fail("cuTensorMapEncodeTiled failed for buffer %d component %d", b, q);
                     return 0;
@@ -644,7 +677,7 @@ int phb_set_spacing(phb_ctx *c, const double *fdx, const double *fdy, const doub
 
 int phb_set_material_table(phb_ctx *c, int32_t nmat, const double *c12, const double *rho) {
     ENTER(c);
-    if (nmat < 1 || nmat > MAX_MAT) return fail("nmat must be 1..%d (got %d)", MAX_MAT, nmat);
+    if (nmat < 1 || nmat > MAX_MAT) return fail("nmat must be 1..%d (got %d)", (int)MAX_MAT, nmat);
     for (int m = 0; m < nmat; ++m)
         if (!(rho[m] > 0)) return fail("density of material %d is not positive", m);
     OK(c->eng->set_table(nmat, c12, rho));
