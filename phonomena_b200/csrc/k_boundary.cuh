@@ -189,11 +189,13 @@ __global__ void k_cls_assign(ClsGeo q, const uint32_t *keys, int nkeys, uint8_t 
     const int l = blockIdx.z;
     if (k >= q.nzp || j >= q.ny || l >= q.nxl + 2) return;
     const uint32_t key = cell_key(q, q.x0 - 1 + l, j, k);
-    int lo = 0, hi = nkeys - 1;
+    // keys[0] is the all-VOID class; keys[1..] are sorted
+    int lo = 1, hi = nkeys - 1;
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
         if (keys[mid] < key) lo = mid + 1; else hi = mid;
     }
+    if (nkeys < 2 || keys[lo] != key) lo = 0;
     code[((long long)l * q.ny + j) * q.nzp + k] = (uint8_t)lo;
 }
 

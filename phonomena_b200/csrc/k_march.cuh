@@ -8,26 +8,32 @@
 //    plays in the usual 2.5-D blocking.  A block owns a (TY rows x 32*V cells) tile of the
 //    (y, z) plane and a chunk of x-planes; warp r of the block is row j0-1+r, so the first
 //    and last warps are the y-halo rows (they only compute stresses).
-//  * u_cur planes arrive by TMA (cp.async.bulk.tensor.3d, UTMALDG in SASS) into an NST-stage
-//    shared-memory ring, box = (34*V, R, 1): one extra 16-byte vector on each side in z gives
-//    the z-halo, and out-of-range rows/columns/planes are zero-filled by the TMA unit, so the
-//    kernel has no load-side boundary code.  One elected thread issues, everybody waits on
-//    the stage's mbarrier.
-//  * Per plane n a thread keeps in registers, per cell: u(n), u(n+1) (own position), the
-//    normal stresses T1..T3(n) and the shear stresses T5(n-1), T6(n-1) carried from the
-//    previous iteration.  Neighbours in y come from shared memory (u from the TMA ring, T2/T4/
-//    T6 from a double-buffered exchange tile: ONE __syncthreads per plane); neighbours in z
-//    come from warp shuffles, and the two edge lanes rebuild the three halo stresses they need
-//    from the ring's halo vectors.
+//  * EVERY input arrives by TMA (cp.async.bulk.tensor.3d -> UTMALDG) into an NST-stage shared
+//    ring, one stage per x-plane: the three u_cur tiles with a 16-byte halo vector on each
+//    side in z and a halo row on each side in y, the three u_old tiles (no halo) and the
+//    1-byte stencil-class tile.  Out-of-range rows / columns / planes are zero-filled by the
+//    TMA unit, so there is no load-side boundary code and no global load instruction in the
+//    plane loop.  Lane 0 of warp 0 is the producer; `full[s]` / `empty[s]` mbarriers gate
+//    the ring.
+//  * There is NO block-wide barrier in the plane loop.  Per plane a row-warp publishes its
+//    T2/T4/T6 (the stresses its y-neighbours need) into a double-buffered exchange tile and
+//    signals the `pub[r][parity]` mbarrier; it then waits only for its two neighbours.
+//    Warps drift by up to one plane, which absorbs memory-latency jitter.
+//  * Per plane a thread keeps in registers, per cell: u(n) (own position), the normal stresses
+//    T1..T3(n) and the shear stresses T5(n-1), T6(n-1) carried from the previous plane.
+//    z-neighbours come from warp shuffles; the two edge lanes rebuild the three halo stresses
+//    they need from the ring's halo vectors.
 //  * The reference's slice ranges ("never written => 0") are not code here: the per-cell
 //    stencil class (1 byte, fd_common.cuh) selects a 16-entry coefficient row in shared memory
 //    that is already zero wherever a stress or an update does not exist.
-//  * u_old, the class byte and u_new are pure streams (16-byte vector LDG/STG, no halo).
+//  * u_new leaves as 16-byte vector stores.
 //
 // Arithmetic goes through the same formula functions as the naive kernel, so in EXACT mode
 // both are bit-identical to the reference.
 #pragma once
 #include <cuda.h>
+
+#include <type_traits>
 
 #include "k_naive.cuh"
 
@@ -40,29 +46,45 @@ template <> struct VecOf<double> { static constexpr int V = 2; };
 template <class T, int R, int NST>
 struct MarchCfg {
     static constexpr int V = VecOf<T>::V;
-    static constexpr int TZ = 32 * V;              // cells per tile row
-    static constexpr int PITCH = 34 * V;           // ring row pitch in elements (halo vector each side)
-    static constexpr int TY = R - 2;               // output rows per tile
-    static constexpr int THREADS = R * 32;
-    static constexpr int STAGE_ELEMS = 3 * R * PITCH;
-    static constexpr size_t STAGE_BYTES = (size_t)STAGE_ELEMS * sizeof(T);
-    static constexpr size_t RING_BYTES = NST * STAGE_BYTES;
-    static constexpr size_t XCH_BYTES = (size_t)2 * 3 * R * TZ * sizeof(T);
-    static constexpr size_t BAR_BYTES = 128;
-    static constexpr size_t smem_bytes(int ncls) {
-        return RING_BYTES + XCH_BYTES + BAR_BYTES + (size_t)ncls * CLS_W * sizeof(T);
-    }
+    static constexpr int SZ = (int)sizeof(T);
+    static constexpr int TZ = 32 * V;                 // cells per tile row
+    static constexpr int TY = R - 2;                  // output rows per tile
+    static constexpr int ROWB = 34 * 16;              // u_cur ring row: 34 vectors of 16 B (halo vector each side)
+    static constexpr int UCOMP = R * ROWB;            // one u_cur component tile
+    static constexpr int OROWB = 32 * 16;             // u_old row (no halo)
+    static constexpr int OCOMP = TY * OROWB;
+    static constexpr int CB = TZ + 32;                // class row: 16 halo bytes each side
+    static constexpr int CTILE = R * CB;
+    static constexpr int OFF_O = 3 * UCOMP;           // stage layout: [U x3][O x3][C]
+    static constexpr int OFF_C = OFF_O + 3 * OCOMP;
+    static constexpr int STAGE = (OFF_C + CTILE + 127) / 128 * 128;
+    static constexpr int XROWB = 32 * 16;
+    static constexpr int XCOMP = R * XROWB;
+    static constexpr int XBUF = 3 * XCOMP;            // T2, T4, T6
+    static constexpr int OFF_X = NST * STAGE;
+    static constexpr int OFF_BAR = OFF_X + 2 * XBUF;
+    static constexpr int NBAR = 2 * NST + 2 * R;      // full[NST], empty[NST], pub[R][2]
+    static constexpr int OFF_SX = OFF_BAR + (NBAR * 8 + 8 + 127) / 128 * 128;   // + the `issued` counter
+    static constexpr uint32_t TX_U = 3u * UCOMP + CTILE;   // bytes per stage without / with u_old
+    static constexpr uint32_t TX_UO = TX_U + 3u * OCOMP;
+    // x-spacing table: 2 values per plane for planes [ia-2, ib+1]; z table [2][TZ]; y table [R][2]; class table
+    __host__ __device__ static size_t off_ztab(int chunk) { return (size_t)OFF_SX + ((size_t)2 * (chunk + 4) * SZ + 127) / 128 * 128; }
+    __host__ __device__ static size_t off_tab(int chunk) { return off_ztab(chunk) + ((size_t)(2 * TZ + 2 * R) * SZ + 127) / 128 * 128; }
+    __host__ __device__ static size_t smem_bytes(int chunk, int ncls) { return off_tab(chunk) + (size_t)ncls * CLS_W * SZ; }
 };
 
-// ---- PTX helpers --------------------------------------------------------------------------------
+// ---- PTX helpers (32-bit shared-window addresses throughout) ------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
@@ -71,36 +93,114 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "@p bra D_%=;\n"
         "bra W_%=;\n"
         "D_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
-__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *tm, uint64_t *bar, int c0, int c1, int c2) {
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int c0, int c1, int c2) {
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+        ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+template <class T, int V> struct alignas(sizeof(T) * V) Pack { T v[V]; };
+
+__device__ __forceinline__ Pack<float, 4> lds_vec(uint32_t a, float) {
+    Pack<float, 4> r;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]) : "r"(a));
+    return r;
+}
+__device__ __forceinline__ Pack<double, 2> lds_vec(uint32_t a, double) {
+    Pack<double, 2> r;
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(r.v[0]), "=d"(r.v[1]) : "r"(a));
+    return r;
+}
+__device__ __forceinline__ void sts_vec(uint32_t a, const Pack<float, 4> &x) {
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(x.v[0]), "f"(x.v[1]), "f"(x.v[2]), "f"(x.v[3]) : "memory");
+}
+__device__ __forceinline__ void sts_vec(uint32_t a, const Pack<double, 2> &x) {
+    asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(a), "d"(x.v[0]), "d"(x.v[1]) : "memory");
+}
+__device__ __forceinline__ float lds1(uint32_t a, float) {
+    float r;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(a));
+    return r;
+}
+__device__ __forceinline__ double lds1(uint32_t a, double) {
+    double r;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(r) : "r"(a));
+    return r;
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
+    uint32_t r;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(r) : "r"(a));
+    return r;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
+    uint32_t r;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(r) : "r"(a));
+    return r;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+    uint32_t r;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(a));
+    return r;
+}
+// Class-row coefficient loads (rows are CLS_W * sizeof(T) bytes, 64/128-byte aligned):
+// entries 0..8 (normal stresses), entries 9..11 (c44 c55 c66), entries 12..14 (rx ry rz).
+__device__ __forceinline__ void lds_c9(uint32_t row, float (&c)[9]) {
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(c[0]), "=f"(c[1]), "=f"(c[2]), "=f"(c[3]) : "r"(row));
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+16];" : "=f"(c[4]), "=f"(c[5]), "=f"(c[6]), "=f"(c[7]) : "r"(row));
+    asm volatile("ld.shared.f32 %0, [%1+32];" : "=f"(c[8]) : "r"(row));
+}
+__device__ __forceinline__ void lds_c9(uint32_t row, double (&c)[9]) {
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(c[0]), "=d"(c[1]) : "r"(row));
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2+16];" : "=d"(c[2]), "=d"(c[3]) : "r"(row));
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2+32];" : "=d"(c[4]), "=d"(c[5]) : "r"(row));
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2+48];" : "=d"(c[6]), "=d"(c[7]) : "r"(row));
+    asm volatile("ld.shared.f64 %0, [%1+64];" : "=d"(c[8]) : "r"(row));
+}
+// four entries starting at a multiple of 4 (9..11 live in entries 8..11, 12..14 in 12..15)
+__device__ __forceinline__ void lds_c4(uint32_t row, int e0, float (&c)[4]) {
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(c[0]), "=f"(c[1]), "=f"(c[2]), "=f"(c[3]) : "r"(row + e0 * 4));
+}
+__device__ __forceinline__ void lds_c4(uint32_t row, int e0, double (&c)[4]) {
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(c[0]), "=d"(c[1]) : "r"(row + e0 * 8));
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2+16];" : "=d"(c[2]), "=d"(c[3]) : "r"(row + e0 * 8));
 }
 
 template <class T> __device__ __forceinline__ T shfl_up1(T v) { return __shfl_up_sync(0xffffffffu, v, 1); }
 template <class T> __device__ __forceinline__ T shfl_dn1(T v) { return __shfl_down_sync(0xffffffffu, v, 1); }
 
-template <class T, int V> struct alignas(sizeof(T) * V) Pack { T v[V]; };
+struct MarchMaps {
+    CUtensorMap u[3];   // u_cur components, box (34 V, R, 1)
+    CUtensorMap o[3];   // u_old components, box (32 V, TY, 1)
+    CUtensorMap c;      // class bytes,      box (32 V + 32, R, 1)
+};
 
 // ---- the kernel ---------------------------------------------------------------------------------
 template <class A, int R, int NST>
 __global__ void __launch_bounds__(R * 32, (R <= 8 ? 2 : 1))
-k_step_march(const __grid_constant__ CUtensorMap tm_ux, const __grid_constant__ CUtensorMap tm_uy,
-             const __grid_constant__ CUtensorMap tm_uz, StepArgs<typename A::T> p, MatCls<typename A::T> m, int chunk) {
+k_step_march(const __grid_constant__ MarchMaps tm, StepArgs<typename A::T> p, MatCls<typename A::T> m, int chunk) {
     using T = typename A::T;
     using C_ = MarchCfg<T, R, NST>;
-    constexpr int V = C_::V, TZ = C_::TZ, PITCH = C_::PITCH, SE = C_::STAGE_ELEMS;
+    constexpr int V = C_::V, SZ = C_::SZ, TZ = C_::TZ;
+    constexpr int UCE = C_::UCOMP / SZ, OCE = C_::OCOMP / SZ, XCE = C_::XCOMP / SZ;   // component strides in elements
+    constexpr int ROWE = C_::ROWB / SZ;
     using PV = Pack<T, V>;
-    using PC = Pack<uint8_t, V>;
+    using CW = typename std::conditional<V == 4, uint32_t, uint16_t>::type;            // V class bytes
     const Geo<T> &g = p.g;
 
     extern __shared__ __align__(1024) unsigned char sm[];
-    T *const ring = reinterpret_cast<T *>(sm);                                      // [NST][3][R][PITCH]
-    T *const xch = reinterpret_cast<T *>(sm + C_::RING_BYTES);                      // [2][3][R][TZ]
-    uint64_t *const bars = reinterpret_cast<uint64_t *>(sm + C_::RING_BYTES + C_::XCH_BYTES);
-    T *const stab = reinterpret_cast<T *>(sm + C_::RING_BYTES + C_::XCH_BYTES + C_::BAR_BYTES);   // [ncls][CLS_W]
+    const uint32_t sb = smem_u32(sm);
 
     const int lane = threadIdx.x & 31, r = threadIdx.x >> 5;
     const int k0t = blockIdx.x * TZ;                 // first cell of the tile row
@@ -111,224 +211,245 @@ k_step_march(const __grid_constant__ CUtensorMap tm_ux, const __grid_constant__ 
     const int j = j0 - 1 + r;
     const int kb = k0t + lane * V;                   // first cell of this lane
     const bool k0c = (kb == 0);                      // element 0 of this thread is the k = 0 plane
-    const int rS = max(r - 1, 0), rN = min(r + 1, R - 1);
+    const int nplanes = (ib - ia) + 2;               // planes ia-1 .. ib, consumed in order q = 0, 1, ...
+    const int lbase = (ia - 1) - g.x0 + 1;           // local plane index of q = 0
 
-    // ---- one-time setup: class table to smem, barriers ----
-    for (int q = threadIdx.x; q < m.ncls * CLS_W; q += R * 32) stab[q] = m.tab[q];
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < NST; ++s) mbar_init(&bars[s], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const uint32_t bar_full = sb + C_::OFF_BAR, bar_empty = bar_full + NST * 8, bar_pub = bar_empty + NST * 8;
+    int *const issued = reinterpret_cast<int *>(sm + C_::OFF_BAR + C_::NBAR * 8);
+    // small tables: x spacings per plane, z spacings per cell of the tile row, y spacings per row
+    T *const sxp = reinterpret_cast<T *>(sm + C_::OFF_SX);                        // [plane-(ia-2)][2] = fdx, sdx
+    T *const ztab = reinterpret_cast<T *>(sm + C_::off_ztab(chunk));              // [2][TZ] = fdz[k], sdz[k-1]
+    T *const ytab = ztab + 2 * TZ;                                                // [R][2]  = fdy[j], sdy[j-1]
+    const T *const stab = reinterpret_cast<const T *>(__builtin_assume_aligned(sm + C_::off_tab(chunk), 128));
+
+    // ---- one-time setup ----
+    {
+        T *tabw = reinterpret_cast<T *>(sm + C_::off_tab(chunk));
+        for (int q = threadIdx.x; q < m.ncls * CLS_W; q += R * 32) tabw[q] = m.tab[q];
+        for (int q = threadIdx.x; q < nplanes + 2; q += R * 32) {
+            const int n = min(max(ia - 2 + q, -1), g.nx);          // tables are addressable on [-1, n]
+            sxp[2 * q + 0] = g.fdx[n];
+            sxp[2 * q + 1] = g.sdx[n];
+        }
+        for (int q = threadIdx.x; q < TZ; q += R * 32) {
+            const int k = min(k0t + q, g.nz);
+            ztab[q] = g.fdz[k];
+            ztab[TZ + q] = (k == 0) ? g.sdz0 : g.sdz[k - 1];       // k = 0 uses sdz[0] (App. B #1)
+        }
+        if (threadIdx.x < R) {
+            const int jj = min(max(j0 - 1 + (int)threadIdx.x, 0), g.ny);
+            ytab[2 * threadIdx.x + 0] = g.fdy[jj];
+            ytab[2 * threadIdx.x + 1] = g.sdy[jj - 1];
+        }
+        if (threadIdx.x == 0) {
+            for (int s = 0; s < NST; ++s) { mbar_init(bar_full + s * 8, 1); mbar_init(bar_empty + s * 8, R); }
+            for (int q = 0; q < 2 * R; ++q) mbar_init(bar_pub + q * 8, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
     }
     __syncthreads();
 
-    // planes are consumed in order q = 0, 1, ...; plane n = ia - 1 + q; local plane l = n - x0 + 1
-    const int nplanes = (ib - ia) + 2;
-    const CUtensorMap *pm0 = &tm_ux, *pm1 = &tm_uy, *pm2 = &tm_uz;
-    const int lbase = (ia - 1) - g.x0 + 1;
-    auto issue = [=](int q) {
+    // producer: plane q -> stage q % NST.  u_old is not needed for the first and the last plane.
+    auto issue = [&](int q) {
         const int s = q % NST;
-        T *dst = ring + s * SE;
-        mbar_expect_tx(&bars[s], (uint32_t)C_::STAGE_BYTES);
-        tma_load_3d(dst + 0 * R * PITCH, pm0, &bars[s], k0t - V, j0 - 1, lbase + q);
-        tma_load_3d(dst + 1 * R * PITCH, pm1, &bars[s], k0t - V, j0 - 1, lbase + q);
-        tma_load_3d(dst + 2 * R * PITCH, pm2, &bars[s], k0t - V, j0 - 1, lbase + q);
-    };
-    if (threadIdx.x == 0) {
-        for (int q = 0; q < NST && q < nplanes; ++q) issue(q);
-    }
-
-    // ---- loop-invariant per-thread quantities ----
-    const bool in_box = (j >= 0 && j < g.ny && kb < g.nzp);      // global vector accesses allowed
-    const bool row_out = (r >= 1 && r <= R - 2) && (j < g.ny);    // this WARP produces u_new (warp-uniform:
-                                                                  // the shuffles below need converged warps)
-    // spacings (or reciprocals).  On the k = 0 plane the reference uses the FIRST element of each
-    // spacing array, on "wrong" axes in the shear terms (App. B #1, #2): folded here into the
-    // values element 0 of the k0c thread uses, so the plane loop has no k = 0 code path except
-    // the per-plane x spacings below.
-    T sfz[V], ssz[V];                                             // fdz[k], sdz[k-1]
+        const uint32_t dst = sb + s * C_::STAGE, bar = bar_full + s * 8;
+        const bool with_old = (q >= 1 && q < nplanes - 1);
+        mbar_expect_tx(bar, with_old ? C_::TX_UO : C_::TX_U);
+        const int l = lbase + q;
 #pragma unroll
-    for (int e = 0; e < V; ++e) {
-        const int kc = min(kb + e, g.nz);                         // tables are addressable on [-1, n]
-        sfz[e] = g.fdz[kc];
-        ssz[e] = g.sdz[kc - 1];
+        for (int q3 = 0; q3 < 3; ++q3) tma_load_3d(dst + q3 * C_::UCOMP, &tm.u[q3], bar, k0t - V, j0 - 1, l);
+        tma_load_3d(dst + C_::OFF_C, &tm.c, bar, k0t - 16, j0 - 1, l);
+        if (with_old) {
+#pragma unroll
+            for (int q3 = 0; q3 < 3; ++q3) tma_load_3d(dst + C_::OFF_O + q3 * C_::OCOMP, &tm.o[q3], bar, k0t, j0, l);
+        }
+    };
+    // `issued` = next plane to hand to the TMA unit.  Nobody blocks to produce: the lane that sees an
+    // `empty[s]` phase complete after its own arrival claims the plane with a CAS and issues it.
+    if (threadIdx.x == 0) {
+        int q = 0;
+        for (; q < NST && q < nplanes; ++q) issue(q);
+        *issued = q;
     }
-    const int jc = min(max(j, 0), g.ny);
-    const T sfy = g.fdy[jc], ssy = g.sdy[jc - 1];
-    if (k0c) ssz[0] = g.sdz0;                                     // normal z-term and ux/uy z-term: sdz[0]
-    const T e0_ssy = k0c ? g.sdy0 : ssy;                          // sdy[0] instead of sdy[j-1]
-    const T e0_t4a = k0c ? g.fdy0 : sfz[0];                       // T4: (uy[k+1]-uy[k]) / fdy[0]
-    const T e0_t4b = k0c ? g.fdz0 : sfy;                          // T4: (uz[j+1]-uz[j]) / fdz[0]
-    const T e0_t5a = k0c ? g.fdx0 : sfz[0];                       // T5: (ux[k+1]-ux[k]) / fdx[0]
-    const T e0_t6a = k0c ? g.fdx0 : sfy;                          // T6: (ux[j+1]-ux[j]) / fdx[0]
-    const T e0_uyb = k0c ? g.fdy0 : sfy;                          // uy: (T2[j+1]-T2[j]) / fdy[0]
-    const T e0_uzc = k0c ? (T)1 : sfz[0];                         // uz: T3[..,1] is NOT divided (App. B #3)
-    // halo columns of the edge lanes (never the k = 0 plane)
-    const int kL = k0t - 1, kR = k0t + TZ;
-    const bool haveL = (lane == 0) && (kL >= 0) && in_box;
-    const bool haveR = (lane == 31) && (kR <= g.nz - 1) && in_box;
-    const T sfzL = haveL ? g.fdz[kL] : (T)1, sszR = haveR ? g.sdz[kR - 1] : (T)1;
+    __syncthreads();
 
-    const T *const own0 = ring + r * PITCH + (lane + 1) * V;      // own vector inside a component tile
-    const T *const ownS = ring + rS * PITCH + (lane + 1) * V;
-    const T *const ownN = ring + rN * PITCH + (lane + 1) * V;
-    const T *const rowp = ring + r * PITCH, *const rowS = ring + rS * PITCH, *const rowN = ring + rN * PITCH;
-    auto vec = [](const T *q) -> PV { return *reinterpret_cast<const PV *>(q); };
+    // ---- loop-invariant per-thread quantities (kept few: everything else is re-read from smem) ----
+    const bool in_box = (j >= 0 && j < g.ny && kb < g.nzp);      // global vector stores allowed
+    const bool row_out = (r >= 1 && r <= R - 2) && (j < g.ny);    // this WARP produces u_new (warp-uniform)
+    const bool haveL = (lane == 0) && (k0t >= 1) && (j >= 0 && j < g.ny);           // halo column kL = k0t-1
+    const bool haveR = (lane == 31) && (k0t + TZ <= g.nz - 1) && (j >= 0 && j < g.ny);   // halo column kR
+    const int eo = r * ROWE + (lane + 1) * V;          // own vector inside a u_cur component tile (elements)
+    const int eS = (r >= 1) ? -ROWE : 0, eN = (r <= R - 2) ? ROWE : 0;            // neighbour rows (clamped)
+    const int xo = r * (TZ) + lane * V;                // own vector inside an exchange component tile
+    const int xS = (r >= 1) ? -TZ : 0, xN = (r <= R - 2) ? TZ : 0;
+    const uint32_t pubO = bar_pub + (uint32_t)r * 16;
+    const T *const zt = ztab + lane * V;               // this lane's z spacings
+    const T *const yt = ytab + 2 * r;
 
     // ---- registers carried across planes ----
-    PV uxc, uyc, uzc;            // u(n) own
     T t1c[V], t2c[V], t3c[V];    // T1..T3(n)
     T t5m[V], t6m[V];            // T5(n-1), T6(n-1)
     T t3R = (T)0;                // T3(n, j, kR) for lane 31
-    PC codec;                    // class(n)
 #pragma unroll
-    for (int e = 0; e < V; ++e) { t1c[e] = t2c[e] = t3c[e] = t5m[e] = t6m[e] = (T)0; codec.v[e] = 0; }
+    for (int e = 0; e < V; ++e) t1c[e] = t2c[e] = t3c[e] = t5m[e] = t6m[e] = (T)0;
 
-    // running element offset of (plane n, row j, cell kb)
-    long long off = (long long)lbase * g.ps + (long long)j * g.nzp + kb;
+    T *pnx = p.nw.ux + ((long long)lbase * g.ps + (long long)j * g.nzp + kb);   // (plane n, j, kb) of u_new
+    const long long dyz = (long long)(p.nw.uy - p.nw.ux), dzz_ = (long long)(p.nw.uz - p.nw.ux);
 
-    // plane q = 0 (n = ia - 1): own values
-    mbar_wait(&bars[0], 0);
-    uxc = vec(own0); uyc = vec(own0 + R * PITCH); uzc = vec(own0 + 2 * R * PITCH);
-    if (in_box) codec = *reinterpret_cast<const PC *>(m.code + off);
+    mbar_wait(bar_full, 0);                           // plane q = 0 (n = ia - 1)
+    int sCi = 0, sNi = 1 % NST;                       // stage indices of plane n and n + 1
+    uint32_t phN = 0;                                 // phase parity of full[sNi] for plane n + 1
 
+#pragma unroll 1
     for (int it = 0; it + 1 < nplanes; ++it) {
         const int n = ia - 1 + it;                    // plane being completed; n + 1 is the newest
         const bool emit = (it >= 1);                  // it = 0 only primes the carried stresses
-        const int sC = (it % NST) * SE, sN = ((it + 1) % NST) * SE;
+        const T *const uC = reinterpret_cast<const T *>(sm + sCi * C_::STAGE);     // plane n tiles
+        const T *const uN = reinterpret_cast<const T *>(sm + sNi * C_::STAGE);     // plane n+1 tiles
+        auto vec = [](const T *q) -> PV { return *reinterpret_cast<const PV *>(q); };
 
-        // (0) streaming operands: class bytes of plane n+1, u_old(n), halo class bytes
-        PV uox, uoy, uoz;
-        PC coden;
-#pragma unroll
-        for (int e = 0; e < V; ++e) { uox.v[e] = uoy.v[e] = uoz.v[e] = (T)0; coden.v[e] = 0; }
-        uint8_t clsL = 0, clsR = 0;
-        if (in_box) {
-            coden = *reinterpret_cast<const PC *>(m.code + off + g.ps);
-            if (emit && row_out) {   // in_box holds here
-                uox = *reinterpret_cast<const PV *>(p.old.ux + off);
-                uoy = *reinterpret_cast<const PV *>(p.old.uy + off);
-                uoz = *reinterpret_cast<const PV *>(p.old.uz + off);
-            }
-            if (haveL) clsL = m.code[off - 1];
-            if (haveR) clsR = m.code[off + g.ps + V];
-        }
+        mbar_wait(bar_full + sNi * 8, phN);
 
-        // per-plane x spacings (uniform); element 0 of the k0c thread uses the first elements
-        const T sfx_n = g.fdx[n], ssx_n = g.sdx[n], ssx_m = g.sdx[max(n - 1, -1)];
-        const T e0_ssx_n = k0c ? g.sdx0 : ssx_n;     // normal(n+1): sdx[0]
-        const T e0_ssx_m = k0c ? g.sdx0 : ssx_m;     // uy, uz: sdx[0]
-        const T e0_sfx_n = k0c ? g.fdx0 : sfx_n;     // ux: fdx[0]
-        const T e0_shb = k0c ? g.fdz0 : sfx_n;       // T5, T6 second term: fdz[0]
+        // per-plane x spacings (uniform); element 0 of the k0c thread uses the first elements (App. B #1, #2)
+        const T sfx_n = sxp[2 * (it + 1) + 0];        // fdx[n]
+        const T ssx_n = sxp[2 * (it + 1) + 1];        // sdx[n]   = sdx[(n+1)-1]
+        const T ssx_m = sxp[2 * it + 1];              // sdx[n-1]
+        const T sfy = yt[0], ssy = yt[1];             // fdy[j], sdy[j-1]
+        const PV zf = vec(zt), zs = vec(zt + TZ);     // fdz[k], sdz[k-1] (k = 0: sdz[0])
 
-        // (1) newest plane
-        mbar_wait(&bars[(it + 1) % NST], ((it + 1) / NST) & 1);
-        const PV uxn = vec(own0 + sN), uyn = vec(own0 + sN + R * PITCH), uzn = vec(own0 + sN + 2 * R * PITCH);
-
-        // (2) normal stresses at plane n + 1
-        const PV uyS = vec(ownS + sN + R * PITCH);                // uy(n+1, j-1)
-        T uzW0 = shfl_up1(uzn.v[V - 1]);                          // uz(n+1, k-1) for element 0
-        if (lane == 0) uzW0 = rowp[sN + 2 * R * PITCH + V - 1];   // ring halo (zero-filled below k = 0)
-        T t1n[V], t2n[V], t3n[V];
-#pragma unroll
-        for (int e = 0; e < V; ++e) {
-            const T dxx = A::sub(uxn.v[e], uxc.v[e]);
-            const T dyy = A::sub(uyn.v[e], uyS.v[e]);
-            const T dzz = A::sub(uzn.v[e], (e == 0) ? uzW0 : uzn.v[e > 0 ? e - 1 : 0]);
-            const T sx = (e == 0) ? e0_ssx_n : ssx_n, sy = (e == 0) ? e0_ssy : ssy;
-            const T *c = stab + (int)coden.v[e] * CLS_W;
-            t1n[e] = normal_row<A>(c + 0, dxx, dyy, dzz, sx, sy, ssz[e]);
-            t2n[e] = normal_row<A>(c + 3, dxx, dyy, dzz, sx, sy, ssz[e]);
-            t3n[e] = normal_row<A>(c + 6, dxx, dyy, dzz, sx, sy, ssz[e]);
-        }
-
-        // (3) shear stresses at plane n
-        const PV uzN = vec(ownN + sC + 2 * R * PITCH), uxN = vec(ownN + sC);   // uz(n, j+1), ux(n, j+1)
-        T uyE = shfl_dn1(uyc.v[0]), uxE = shfl_dn1(uxc.v[0]);                  // uy(n, k+1), ux(n, k+1) for element V-1
-        if (lane == 31) { uyE = rowp[sC + R * PITCH + 33 * V]; uxE = rowp[sC + 33 * V]; }
+        // (1) shear stresses at plane n
         T t4[V], t5[V], t6[V];
+        T t4L = (T)0, t5L = (T)0;
+        const PV uxc = vec(uC + eo), uyc = vec(uC + UCE + eo), uzc = vec(uC + 2 * UCE + eo);
+        const CW cwc = *reinterpret_cast<const CW *>(sm + sCi * C_::STAGE + C_::OFF_C + r * C_::CB + 16 + lane * V);
+        {
+            const PV uyn = vec(uN + UCE + eo), uzn = vec(uN + 2 * UCE + eo);
+            const PV uzN = vec(uC + 2 * UCE + eo + eN), uxN = vec(uC + eo + eN);     // uz(n, j+1), ux(n, j+1)
+            T uyE = shfl_dn1(uyc.v[0]), uxE = shfl_dn1(uxc.v[0]);                    // uy(n, k+1), ux(n, k+1)
+            if (lane == 31) { uyE = uC[UCE + r * ROWE + 33 * V]; uxE = uC[r * ROWE + 33 * V]; }
+            const T shb0 = k0c ? g.fdz0 : sfx_n;       // T5, T6 second term on k = 0: fdz[0]
 #pragma unroll
-        for (int e = 0; e < V; ++e) {
-            const T uye = (e == V - 1) ? uyE : uyc.v[e < V - 1 ? e + 1 : e];
-            const T uxe = (e == V - 1) ? uxE : uxc.v[e < V - 1 ? e + 1 : e];
-            const T *c = stab + (int)codec.v[e] * CLS_W;
-            const T shb = (e == 0) ? e0_shb : sfx_n;
-            t4[e] = shear<A>(c[CLS_C44], A::sub(uye, uyc.v[e]), (e == 0) ? e0_t4a : sfz[e],
-                             A::sub(uzN.v[e], uzc.v[e]), (e == 0) ? e0_t4b : sfy);
-            t5[e] = shear<A>(c[CLS_C55], A::sub(uxe, uxc.v[e]), (e == 0) ? e0_t5a : sfz[e],
-                             A::sub(uzn.v[e], uzc.v[e]), shb);
-            t6[e] = shear<A>(c[CLS_C66], A::sub(uxN.v[e], uxc.v[e]), (e == 0) ? e0_t6a : sfy,
-                             A::sub(uyn.v[e], uyc.v[e]), shb);
+            for (int e = 0; e < V; ++e) {
+                const T uye = (e == V - 1) ? uyE : uyc.v[e < V - 1 ? e + 1 : e];
+                const T uxe = (e == V - 1) ? uxE : uxc.v[e < V - 1 ? e + 1 : e];
+                const T *c = stab + (int)((cwc >> (8 * e)) & 255u) * CLS_W;
+                const bool k0 = (e == 0) && k0c;
+                const T shb = (e == 0) ? shb0 : sfx_n;
+                t4[e] = shear<A>(c[CLS_C44], A::sub(uye, uyc.v[e]), k0 ? g.fdy0 : zf.v[e],
+                                 A::sub(uzN.v[e], uzc.v[e]), k0 ? g.fdz0 : sfy);
+                t5[e] = shear<A>(c[CLS_C55], A::sub(uxe, uxc.v[e]), k0 ? g.fdx0 : zf.v[e],
+                                 A::sub(uzn.v[e], uzc.v[e]), shb);
+                t6[e] = shear<A>(c[CLS_C66], A::sub(uxN.v[e], uxc.v[e]), k0 ? g.fdx0 : sfy,
+                                 A::sub(uyn.v[e], uyc.v[e]), shb);
+            }
+            if (haveL) {   // T4, T5 at (n, j, kL) for the first element's uy / ux update (never k = 0)
+                const T *c = stab + (int)sm[sCi * C_::STAGE + C_::OFF_C + r * C_::CB + 15] * CLS_W;
+                const T *h = uC + r * ROWE + V - 1;
+                const T uxL = h[0], uyL = h[UCE], uzL = h[2 * UCE], uzLN = h[2 * UCE + eN];
+                const T uzLn = uN[2 * UCE + r * ROWE + V - 1];
+                const T sfzL = g.fdz[k0t - 1];
+                t4L = shear<A>(c[CLS_C44], A::sub(uyc.v[0], uyL), sfzL, A::sub(uzLN, uzL), sfy);
+                t5L = shear<A>(c[CLS_C55], A::sub(uxc.v[0], uxL), sfzL, A::sub(uzLn, uzL), sfx_n);
+            }
         }
 
-        // (4) halo stresses of the edge lanes: columns kL = k0t-1 (T4, T5 at plane n) and
-        //     kR = k0t+TZ (T3 at plane n+1)
-        T t4L = (T)0, t5L = (T)0, t3Rn = (T)0;
-        if (haveL) {
-            const T *c = stab + (int)clsL * CLS_W;
-            const T uyL = rowp[sC + R * PITCH + V - 1], uzL = rowp[sC + 2 * R * PITCH + V - 1], uxL = rowp[sC + V - 1];
-            const T uzLN = rowN[sC + 2 * R * PITCH + V - 1], uzLn = rowp[sN + 2 * R * PITCH + V - 1];
-            t4L = shear<A>(c[CLS_C44], A::sub(uyc.v[0], uyL), sfzL, A::sub(uzLN, uzL), sfy);
-            t5L = shear<A>(c[CLS_C55], A::sub(uxc.v[0], uxL), sfzL, A::sub(uzLn, uzL), sfx_n);
-        }
-        if (haveR) {
-            const T *c = stab + (int)clsR * CLS_W;
-            const T dxx = A::sub(rowp[sN + 33 * V], rowp[sC + 33 * V]);
-            const T dyy = A::sub(rowp[sN + R * PITCH + 33 * V], rowS[sN + R * PITCH + 33 * V]);
-            const T dzz = A::sub(rowp[sN + 2 * R * PITCH + 33 * V], uzn.v[V - 1]);
-            t3Rn = normal_row<A>(c + 6, dxx, dyy, dzz, ssx_n, ssy, sszR);
-        }
-
-        // (5) publish T2(n), T4(n), T6(n) for the y-neighbours; one barrier per plane
-        T *const xb = xch + (it & 1) * (3 * R * TZ) + lane * V;
+        // (2) publish T2(n), T4(n), T6(n) for the y-neighbours and signal them
+        T *const xb = reinterpret_cast<T *>(sm + C_::OFF_X + (it & 1) * C_::XBUF) + xo;
         {
             PV a, b, c;
 #pragma unroll
             for (int e = 0; e < V; ++e) { a.v[e] = t2c[e]; b.v[e] = t4[e]; c.v[e] = t6[e]; }
-            *reinterpret_cast<PV *>(xb + (0 * R + r) * TZ) = a;
-            *reinterpret_cast<PV *>(xb + (1 * R + r) * TZ) = b;
-            *reinterpret_cast<PV *>(xb + (2 * R + r) * TZ) = c;
+            *reinterpret_cast<PV *>(xb) = a;
+            *reinterpret_cast<PV *>(xb + XCE) = b;
+            *reinterpret_cast<PV *>(xb + 2 * XCE) = c;
         }
-        __syncthreads();
-        // every read of ring stage it % NST is done: refill it with plane it + NST
-        if (threadIdx.x == 0 && it + NST < nplanes) issue(it + NST);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(pubO + (it & 1) * 8);
+
+        // (3) normal stresses at plane n + 1 (overlaps the neighbours' publishing)
+        T t1n[V], t2n[V], t3n[V];
+        T t3Rn = (T)0;
+        {
+            const PV uxn = vec(uN + eo), uyn = vec(uN + UCE + eo), uzn = vec(uN + 2 * UCE + eo);
+            const PV uyS = vec(uN + UCE + eo + eS);                              // uy(n+1, j-1)
+            T uzW0 = shfl_up1(uzn.v[V - 1]);                                     // uz(n+1, k-1) for element 0
+            if (lane == 0) uzW0 = uN[2 * UCE + r * ROWE + V - 1];                // ring halo (0 below k = 0)
+            const CW cwn = *reinterpret_cast<const CW *>(sm + sNi * C_::STAGE + C_::OFF_C + r * C_::CB + 16 + lane * V);
+#pragma unroll
+            for (int e = 0; e < V; ++e) {
+                const bool k0 = (e == 0) && k0c;
+                const T dxx = A::sub(uxn.v[e], uxc.v[e]);
+                const T dyy = A::sub(uyn.v[e], uyS.v[e]);
+                const T dzz = A::sub(uzn.v[e], (e == 0) ? uzW0 : uzn.v[e > 0 ? e - 1 : 0]);
+                const T sx = k0 ? g.sdx0 : ssx_n, sy = k0 ? g.sdy0 : ssy;
+                const T *c = stab + (int)((cwn >> (8 * e)) & 255u) * CLS_W;
+                t1n[e] = normal_row<A>(c + 0, dxx, dyy, dzz, sx, sy, zs.v[e]);
+                t2n[e] = normal_row<A>(c + 3, dxx, dyy, dzz, sx, sy, zs.v[e]);
+                t3n[e] = normal_row<A>(c + 6, dxx, dyy, dzz, sx, sy, zs.v[e]);
+            }
+            if (haveR) {   // T3(n+1, j, kR) for the next plane's uz update of the last element (never k = 0)
+                const T *c = stab + (int)sm[sNi * C_::STAGE + C_::OFF_C + r * C_::CB + 16 + TZ] * CLS_W;
+                const T *hC = uC + r * ROWE + 33 * V, *hN = uN + r * ROWE + 33 * V;
+                const T dxx = A::sub(hN[0], hC[0]);
+                const T dyy = A::sub(hN[UCE], hN[UCE + eS]);
+                const T dzz = A::sub(hN[2 * UCE], uzn.v[V - 1]);
+                t3Rn = normal_row<A>(c + 6, dxx, dyy, dzz, ssx_n, ssy, g.sdz[k0t + TZ - 1]);
+            }
+        }
+
+        // wait for both neighbours' plane-n stresses (also bounds the drift between warps)
+        {
+            const uint32_t ph = (it >> 1) & 1;
+            if (r >= 1) mbar_wait(pubO - 16 + (it & 1) * 8, ph);
+            if (r <= R - 2) mbar_wait(pubO + 16 + (it & 1) * 8, ph);
+        }
 
         if (emit && row_out) {
-            // (6) y-neighbour stresses
-            const PV t2N = vec(xb + (0 * R + rN) * TZ);
-            const PV t4S = vec(xb + (1 * R + rS) * TZ);
-            const PV t6S = vec(xb + (2 * R + rS) * TZ);
-            // (7) z-neighbour stresses
+            // (4) z-neighbour stresses
             T t3U = shfl_dn1(t3c[0]);                 // T3(n, k+1) for element V-1
             T t4W = shfl_up1(t4[V - 1]);              // T4(n, k-1) for element 0
             T t5W = shfl_up1(t5[V - 1]);              // T5(n, k-1) for element 0
             if (lane == 31) t3U = t3R;
             if (lane == 0) { t4W = t4L; t5W = t5L; }  // zero below the k = 0 plane
-            // (8) displacement update of plane n
+            const T *const oC = uC + (C_::OFF_O / SZ) + (r - 1) * TZ + lane * V;   // u_old(n) own vectors
             PV ox, oy, oz;
+            {   // (5) ux
+                const PV t6S = vec(xb + 2 * XCE + xS), uo = vec(oC);
 #pragma unroll
-            for (int e = 0; e < V; ++e) {
-                const T *c = stab + (int)codec.v[e] * CLS_W;
-                const T t3u = (e == V - 1) ? t3U : t3c[e < V - 1 ? e + 1 : e];
-                const T t4w = (e == 0) ? t4W : t4[e > 0 ? e - 1 : 0];
-                const T t5w = (e == 0) ? t5W : t5[e > 0 ? e - 1 : 0];
-                const T sy_s = (e == 0) ? e0_ssy : ssy;
-                {   // ux
-                    const T acc = A::add(A::add(A::scl(A::sub(t1n[e], t1c[e]), (e == 0) ? e0_sfx_n : sfx_n),
-                                                A::scl(A::sub(t6[e], t6S.v[e]), sy_s)),
-                                         A::scl(A::sub(t5[e], t5w), ssz[e]));
-                    ox.v[e] = advance<A>(uxc.v[e], uox.v[e], c[CLS_RX], acc);
+                for (int e = 0; e < V; ++e) {
+                    const bool k0 = (e == 0) && k0c;
+                    const T *c = stab + (int)((cwc >> (8 * e)) & 255u) * CLS_W;
+                    const T t5w = (e == 0) ? t5W : t5[e > 0 ? e - 1 : 0];
+                    const T acc = A::add(A::add(A::scl(A::sub(t1n[e], t1c[e]), k0 ? g.fdx0 : sfx_n),
+                                                A::scl(A::sub(t6[e], t6S.v[e]), k0 ? g.sdy0 : ssy)),
+                                         A::scl(A::sub(t5[e], t5w), zs.v[e]));
+                    ox.v[e] = advance<A>(uxc.v[e], uo.v[e], c[CLS_RX], acc);
                 }
-                {   // uy
-                    const T acc = A::add(A::add(A::scl(A::sub(t6[e], t6m[e]), (e == 0) ? e0_ssx_m : ssx_m),
-                                                A::scl(A::sub(t2N.v[e], t2c[e]), (e == 0) ? e0_uyb : sfy)),
-                                         A::scl(A::sub(t4[e], t4w), ssz[e]));
-                    oy.v[e] = advance<A>(uyc.v[e], uoy.v[e], c[CLS_RY], acc);
+            }
+            {   // (6) uy
+                const PV t2N = vec(xb + xN), uo = vec(oC + OCE);
+#pragma unroll
+                for (int e = 0; e < V; ++e) {
+                    const bool k0 = (e == 0) && k0c;
+                    const T *c = stab + (int)((cwc >> (8 * e)) & 255u) * CLS_W;
+                    const T t4w = (e == 0) ? t4W : t4[e > 0 ? e - 1 : 0];
+                    const T acc = A::add(A::add(A::scl(A::sub(t6[e], t6m[e]), k0 ? g.sdx0 : ssx_m),
+                                                A::scl(A::sub(t2N.v[e], t2c[e]), k0 ? g.fdy0 : sfy)),
+                                         A::scl(A::sub(t4[e], t4w), zs.v[e]));
+                    oy.v[e] = advance<A>(uyc.v[e], uo.v[e], c[CLS_RY], acc);
                 }
-                {   // uz
-                    const T acc = A::add(A::add(A::scl(A::sub(t5[e], t5m[e]), (e == 0) ? e0_ssx_m : ssx_m),
-                                                A::scl(A::sub(t4[e], t4S.v[e]), sy_s)),
-                                         A::scl(A::sub(t3u, t3c[e]), (e == 0) ? e0_uzc : sfz[e]));
-                    oz.v[e] = advance<A>(uzc.v[e], uoz.v[e], c[CLS_RZ], acc);
+            }
+            {   // (7) uz   (k = 0: "+ T3[..,1] - T3[..,0]/fdz[0]", T3[..,1] NOT divided, App. B #3)
+                const PV t4S = vec(xb + XCE + xS), uo = vec(oC + 2 * OCE);
+#pragma unroll
+                for (int e = 0; e < V; ++e) {
+                    const bool k0 = (e == 0) && k0c;
+                    const T *c = stab + (int)((cwc >> (8 * e)) & 255u) * CLS_W;
+                    const T t3u = (e == V - 1) ? t3U : t3c[e < V - 1 ? e + 1 : e];
+                    const T acc = A::add(A::add(A::scl(A::sub(t5[e], t5m[e]), k0 ? g.sdx0 : ssx_m),
+                                                A::scl(A::sub(t4[e], t4S.v[e]), k0 ? g.sdy0 : ssy)),
+                                         A::scl(A::sub(t3u, t3c[e]), k0 ? (T)1 : zf.v[e]));
+                    oz.v[e] = advance<A>(uzc.v[e], uo.v[e], c[CLS_RZ], acc);
                 }
             }
             // i = 0: uy, uz keep u_new == u (App. B #9); uz(0, j, 0) is the pre-source value
@@ -338,17 +459,30 @@ k_step_march(const __grid_constant__ CUtensorMap tm_ux, const __grid_constant__ 
                 if (k0c && p.line_save) oz.v[0] = p.line_save[j];
             }
             if (in_box) {
-                *reinterpret_cast<PV *>(p.nw.ux + off) = ox;
-                *reinterpret_cast<PV *>(p.nw.uy + off) = oy;
-                *reinterpret_cast<PV *>(p.nw.uz + off) = oz;
+                *reinterpret_cast<PV *>(pnx) = ox;
+                *reinterpret_cast<PV *>(pnx + dyz) = oy;
+                *reinterpret_cast<PV *>(pnx + dzz_) = oz;
+            }
+        }
+        // every read this warp makes of the stage holding plane n is done
+        __syncwarp();
+        if (lane == 0) {
+            mbar_arrive(bar_empty + sCi * 8);
+            // refill every stage whose readers are all done (usually the one just released by the
+            // slowest warp of plane `it`)
+            for (;;) {
+                const int q = *reinterpret_cast<volatile int *>(issued);
+                if (q >= nplanes) break;
+                if (!mbar_test(bar_empty + (q % NST) * 8, (uint32_t)((q / NST - 1) & 1))) break;
+                if (atomicCAS(issued, q, q + 1) == q) issue(q);
             }
         }
 
-        // (9) rotate the carried registers
-        uxc = uxn; uyc = uyn; uzc = uzn;
-        codec = coden;
+        // (8) rotate
         t3R = t3Rn;
-        off += g.ps;
+        pnx += g.ps;
+        sCi = sNi;
+        if (++sNi == NST) { sNi = 0; phN ^= 1u; }
 #pragma unroll
         for (int e = 0; e < V; ++e) { t1c[e] = t1n[e]; t2c[e] = t2n[e]; t3c[e] = t3n[e]; t5m[e] = t5[e]; t6m[e] = t6[e]; }
     }
@@ -371,42 +505,55 @@ inline PFN_encodeTiled get_encode_tiled() {
     return fn;
 }
 
-// Tensor map over one displacement component: dims (nzp, ny, planes), box (34 V, R, 1).
-template <class T>
-inline bool make_field_map(CUtensorMap *tm, void *base, int nzp, int ny, int planes, int R) {
+// 3-D tensor map over a (planes, ny, nzp) box of `esz`-byte elements with box (bx, by, 1).
+inline bool make_map3(CUtensorMap *tm, CUtensorMapDataType dt, int esz, void *base, int nzp, int ny, int planes, int bx,
+                      int by) {
     PFN_encodeTiled enc = get_encode_tiled();
     if (!enc) return false;
-    constexpr int V = VecOf<T>::V;
     const cuuint64_t dims[3] = {(cuuint64_t)nzp, (cuuint64_t)ny, (cuuint64_t)planes};
-    const cuuint64_t strides[2] = {(cuuint64_t)nzp * sizeof(T), (cuuint64_t)nzp * ny * sizeof(T)};
-    const cuuint32_t box[3] = {(cuuint32_t)(34 * V), (cuuint32_t)R, 1u};
+    const cuuint64_t strides[2] = {(cuuint64_t)nzp * esz, (cuuint64_t)nzp * ny * esz};
+    const cuuint32_t box[3] = {(cuuint32_t)bx, (cuuint32_t)by, 1u};
     const cuuint32_t estr[3] = {1u, 1u, 1u};
-    const CUtensorMapDataType dt = sizeof(T) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
     return enc(tm, dt, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+template <class T>
+inline bool make_field_maps(CUtensorMap *cur_box, CUtensorMap *old_box, void *base, int nzp, int ny, int planes, int R) {
+    constexpr int V = VecOf<T>::V;
+    const CUtensorMapDataType dt = sizeof(T) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    return make_map3(cur_box, dt, sizeof(T), base, nzp, ny, planes, 34 * V, R) &&
+           make_map3(old_box, dt, sizeof(T), base, nzp, ny, planes, 32 * V, R - 2);
+}
+template <class T>
+inline bool make_class_map(CUtensorMap *tm, void *base, int nzp, int ny, int planes, int R) {
+    return make_map3(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, base, nzp, ny, planes, 32 * VecOf<T>::V + 32, R);
 }
 
 template <class T> inline const char *march_name() { return "march_tma"; }
 
+// returns launches made (1), 0 for an empty range, -1 if the shared-memory request is refused
 template <class A, int R, int NST>
-inline int launch_march_cfg(const StepArgs<typename A::T> &p, const MatCls<typename A::T> &m, const CUtensorMap *maps,
+inline int launch_march_cfg(const StepArgs<typename A::T> &p, const MatCls<typename A::T> &m, const MarchMaps &maps,
                             int chunks, cudaStream_t st) {
     using T = typename A::T;
     using C_ = MarchCfg<T, R, NST>;
     auto kern = k_step_march<A, R, NST>;
     static size_t attr_bytes = 0;   // per template instantiation
-    const size_t smem = C_::smem_bytes(m.ncls);
-    if (smem > attr_bytes) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-        attr_bytes = smem;
-    }
     const int np = p.i_end - p.i_begin;
     if (np <= 0) return 0;
     if (chunks < 1) chunks = 1;
     if (chunks > np) chunks = np;
     const int chunk = (np + chunks - 1) / chunks;
+    const size_t smem = C_::smem_bytes(chunk, m.ncls);
+    if (smem > attr_bytes) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+            cudaGetLastError();
+            return -1;
+        }
+        attr_bytes = smem;
+    }
     dim3 grid((p.g.nzp + C_::TZ - 1) / C_::TZ, (p.g.ny + C_::TY - 1) / C_::TY, (np + chunk - 1) / chunk);
-    kern<<<grid, R * 32, smem, st>>>(maps[0], maps[1], maps[2], p, m, chunk);
+    kern<<<grid, R * 32, smem, st>>>(maps, p, m, chunk);
     return 1;
 }
 

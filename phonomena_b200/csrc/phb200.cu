@@ -148,7 +148,7 @@ struct phb_ctx {
     std::vector<long long> slot_tt;
     std::atomic<long long> produced{0}, consumed{0}, released{0};
     // marching kernel: TMA descriptors per [buffer][component], tile plan
-    CUtensorMap maps[3][3];
+    MarchMaps mm[3];           // indexed by the buffer that holds u_cur
     bool maps_ok = false;
     int mR = 16, mNST = 3, mChunks = 0;
     IEngine *eng = nullptr;
@@ -249,7 +249,13 @@ struct Engine : IEngine {
         if (e != cudaSuccess) { cudaFree(slots); CU(e); }
         std::vector<uint32_t> keys;
         for (uint32_t v : hs) if (v != CLS_EMPTY) keys.push_back(v);
-        std::sort(keys.begin(), keys.end());
+        {   // class 0 is always the all-VOID class (what zero-filled out-of-range class bytes select)
+            int fv[7] = {MAT_VOID, MAT_VOID, MAT_VOID, MAT_VOID, MAT_VOID, MAT_VOID, MAT_VOID};
+            const uint32_t vk = cls_key(fv, false);
+            keys.erase(std::remove(keys.begin(), keys.end(), vk), keys.end());
+            std::sort(keys.begin(), keys.end());
+            keys.insert(keys.begin(), vk);
+        }
         cudaFree(slots);
         if (hovf || keys.size() > MAX_CLS)
             return fail("more than %d distinct material stencil classes (%zu found): medium too heterogeneous for the "
@@ -287,7 +293,7 @@ struct Engine : IEngine {
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->st);
         cudaFree(dkeys);
         CU(e);
-        return 0;
+        return make_maps();
     }
 
     int set_abc(const double *k) override {
@@ -389,11 +395,12 @@ struct Engine : IEngine {
         MatCls<T> m = mat();
         auto run = [&]<class A>() -> int {
             if (march) {
-                const CUtensorMap *mp = c->maps[b_cur()];
+                const MarchMaps &mp = c->mm[b_cur()];
                 const int ch = plan_chunks(ie - ib);
                 int r = -2;
                 if (c->mR == 16 && c->mNST == 3) r = launch_march_cfg<A, 16, 3>(p, m, mp, ch, c->st);
-                else if (c->mR == 16 && c->mNST == 4) r = launch_march_cfg<A, 16, 4>(p, m, mp, ch, c->st);
+                else if (c->mR == 16 && c->mNST == 2) r = launch_march_cfg<A, 16, 2>(p, m, mp, ch, c->st);
+                else if (c->mR == 8 && c->mNST == 3) r = launch_march_cfg<A, 8, 3>(p, m, mp, ch, c->st);
                 else if (c->mR == 8 && c->mNST == 4) r = launch_march_cfg<A, 8, 4>(p, m, mp, ch, c->st);
                 if (r == -2) return fail("no marching-kernel instantiation for R=%d NST=%d", c->mR, c->mNST);
                 if (r < 0) return fail("marching kernel needs more shared memory than the device allows (%d classes)", c->ncls);
@@ -422,6 +429,7 @@ struct Engine : IEngine {
         int best = 1;
         double best_eff = 0;
         for (int ch = 1; ch <= 16 && ch * 8 <= np; ++ch) {
+            if (ch < 16 && (np + ch - 1) / ch > 1024) continue;   // x-spacing table lives in shared memory
             const long long blocks = tiles * ch, waves = (blocks + slots - 1) / slots;
             const double eff = (double)blocks / (double)(waves * slots) * (1.0 - 1.5 * ch / (double)np);
             if (eff > best_eff + 1e-9) { best_eff = eff; best = ch; }
@@ -430,18 +438,26 @@ struct Engine : IEngine {
     }
     int make_maps() override {
         c->maps_ok = false;
-        if (c->cfg.kernel == PHB_KERNEL_NAIVE) return 0;
-        for (int b = 0; b < 3; ++b)
-            for (int q = 0; q < 3; ++q) {
-                bool ok = make_field_map<T>(&c->maps[b][q], c->buf[b][q], c->nzp, c->cfg.ny, c->cfg.nxl + 2, c->mR);
-                if (!ok) {
-                    if (c->cfg.kernel == PHB_KERNEL_MARCH) return fail("cuTensorMapEncodeTiled failed for buffer %d component %d", b, q);
-                    return 0;
-                }
-            }
+        if (c->cfg.kernel == PHB_KERNEL_NAIVE || !c->code) return 0;
+        const int planes = c->cfg.nxl + 2;
+        CUtensorMap cur[3][3], old[3][3], cls;
+        bool ok = make_class_map<T>(&cls, c->code, c->nzp, c->cfg.ny, planes, c->mR);
+        for (int b = 0; b < 3 && ok; ++b)
+            for (int q = 0; q < 3 && ok; ++q)
+                ok = make_field_maps<T>(&cur[b][q], &old[b][q], c->buf[b][q], c->nzp, c->cfg.ny, planes, c->mR);
+        if (!ok) {
+            if (c->cfg.kernel == PHB_KERNEL_MARCH) return fail("cuTensorMapEncodeTiled failed");
+            return 0;
+        }
+        for (int b = 0; b < 3; ++b) {
+            const int bo = (b + 2) % 3;
+            for (int q = 0; q < 3; ++q) { c->mm[b].u[q] = cur[b][q]; c->mm[b].o[q] = old[bo][q]; }
+            c->mm[b].c = cls;
+        }
         c->maps_ok = true;
         return 0;
     }
+
     const char *kernel_name() override { return use_march() ? march_name<T>() : "naive"; }
 
     AbcArgs<T> abc_args(int ib, int ie) {
@@ -618,7 +634,6 @@ int phb_create(const phb_cfg *cfg, phb_ctx **out) {
     if (const char *e = getenv("PHB_MARCH_NST")) c->mNST = atoi(e);
     if (const char *e = getenv("PHB_MARCH_CHUNKS")) c->mChunks = atoi(e);
     if (c->mR != 8 && c->mR != 16) return cleanup(fail("PHB_MARCH_R must be 8 or 16"));
-    if (c->eng->make_maps()) return cleanup(1);
     // recorder ring
     if (cfg->record_mask) {
         const int npx = std::max(0, std::min(cfg->x0 + cfg->nxl, cfg->nx - 1) - cfg->x0);
