@@ -47,6 +47,7 @@ template <class T, int R, int NST>
 struct MarchCfg {
     static constexpr int V = VecOf<T>::V;
     static constexpr int SZ = (int)sizeof(T);
+    static constexpr int NSO = 2;                     // depth of the u_old ring
     static constexpr int TZ = 32 * V;                 // cells per tile row
     static constexpr int TY = R - 2;                  // output rows per tile
     static constexpr int ROWB = 34 * 16;              // u_cur ring row: 34 vectors of 16 B (halo vector each side)
@@ -55,18 +56,19 @@ struct MarchCfg {
     static constexpr int OCOMP = TY * OROWB;
     static constexpr int CB = TZ + 32;                // class row: 16 halo bytes each side
     static constexpr int CTILE = R * CB;
-    static constexpr int OFF_O = 3 * UCOMP;           // stage layout: [U x3][O x3][C]
-    static constexpr int OFF_C = OFF_O + 3 * OCOMP;
+    static constexpr int OFF_C = 3 * UCOMP;           // u_cur stage layout: [U x3][C]
     static constexpr int STAGE = (OFF_C + CTILE + 127) / 128 * 128;
+    static constexpr int OSTAGE = 3 * OCOMP;          // u_old stage layout: [O x3]
+    static constexpr int OFF_O = NST * STAGE;
     static constexpr int XROWB = 32 * 16;
     static constexpr int XCOMP = R * XROWB;
     static constexpr int XBUF = 3 * XCOMP;            // T2, T4, T6
-    static constexpr int OFF_X = NST * STAGE;
+    static constexpr int OFF_X = OFF_O + NSO * OSTAGE;
     static constexpr int OFF_BAR = OFF_X + 2 * XBUF;
-    static constexpr int NBAR = 2 * NST + 2 * R;      // full[NST], empty[NST], pub[R][2]
+    static constexpr int NBAR = 2 * NST + NSO + 2 * R;   // full[NST], done[NST], fullO[NSO], pub[R][2]
     static constexpr int OFF_SX = OFF_BAR + (NBAR * 8 + 8 + 127) / 128 * 128;   // + the `issued` counter
-    static constexpr uint32_t TX_U = 3u * UCOMP + CTILE;   // bytes per stage without / with u_old
-    static constexpr uint32_t TX_UO = TX_U + 3u * OCOMP;
+    static constexpr uint32_t TX_U = 3u * UCOMP + CTILE;   // bytes per u_cur stage / u_old stage
+    static constexpr uint32_t TX_O = 3u * OCOMP;
     // x-spacing table: 2 values per plane for planes [ia-2, ib+1]; z table [2][TZ]; y table [R][2]; class table
     __host__ __device__ static size_t off_ztab(int chunk) { return (size_t)OFF_SX + ((size_t)2 * (chunk + 4) * SZ + 127) / 128 * 128; }
     __host__ __device__ static size_t off_tab(int chunk) { return off_ztab(chunk) + ((size_t)(2 * TZ + 2 * R) * SZ + 127) / 128 * 128; }
@@ -194,6 +196,7 @@ k_step_march(const __grid_constant__ MarchMaps tm, StepArgs<typename A::T> p, Ma
     using C_ = MarchCfg<T, R, NST>;
     constexpr int V = C_::V, SZ = C_::SZ, TZ = C_::TZ;
     constexpr int UCE = C_::UCOMP / SZ, OCE = C_::OCOMP / SZ, XCE = C_::XCOMP / SZ;   // component strides in elements
+    static_assert(NST > C_::NSO, "u_cur ring must be deeper than the u_old ring");
     constexpr int ROWE = C_::ROWB / SZ;
     using PV = Pack<T, V>;
     using CW = typename std::conditional<V == 4, uint32_t, uint16_t>::type;            // V class bytes
@@ -214,7 +217,9 @@ k_step_march(const __grid_constant__ MarchMaps tm, StepArgs<typename A::T> p, Ma
     const int nplanes = (ib - ia) + 2;               // planes ia-1 .. ib, consumed in order q = 0, 1, ...
     const int lbase = (ia - 1) - g.x0 + 1;           // local plane index of q = 0
 
-    const uint32_t bar_full = sb + C_::OFF_BAR, bar_empty = bar_full + NST * 8, bar_pub = bar_empty + NST * 8;
+    constexpr int NSO = C_::NSO;
+    const uint32_t bar_full = sb + C_::OFF_BAR, bar_empty = bar_full + NST * 8, bar_fullO = bar_empty + NST * 8,
+                   bar_pub = bar_fullO + NSO * 8;
     int *const issued = reinterpret_cast<int *>(sm + C_::OFF_BAR + C_::NBAR * 8);
     // small tables: x spacings per plane, z spacings per cell of the tile row, y spacings per row
     T *const sxp = reinterpret_cast<T *>(sm + C_::OFF_SX);                        // [plane-(ia-2)][2] = fdx, sdx
@@ -243,33 +248,44 @@ k_step_march(const __grid_constant__ MarchMaps tm, StepArgs<typename A::T> p, Ma
         }
         if (threadIdx.x == 0) {
             for (int s = 0; s < NST; ++s) { mbar_init(bar_full + s * 8, 1); mbar_init(bar_empty + s * 8, R); }
+            for (int s = 0; s < NSO; ++s) mbar_init(bar_fullO + s * 8, 1);
             for (int q = 0; q < 2 * R; ++q) mbar_init(bar_pub + q * 8, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
     }
     __syncthreads();
 
-    // producer: plane q -> stage q % NST.  u_old is not needed for the first and the last plane.
-    auto issue = [&](int q) {
+    // producer: u_cur/class plane q -> stage q % NST; u_old plane q -> stage q % NSO, issued NST-NSO planes
+    // later (it is only needed in the second half of iteration q and must not hold a deep ring).
+    auto issue_u = [&](int q) {
         const int s = q % NST;
         const uint32_t dst = sb + s * C_::STAGE, bar = bar_full + s * 8;
-        const bool with_old = (q >= 1 && q < nplanes - 1);
-        mbar_expect_tx(bar, with_old ? C_::TX_UO : C_::TX_U);
-        const int l = lbase + q;
+        mbar_expect_tx(bar, C_::TX_U);
 #pragma unroll
-        for (int q3 = 0; q3 < 3; ++q3) tma_load_3d(dst + q3 * C_::UCOMP, &tm.u[q3], bar, k0t - V, j0 - 1, l);
-        tma_load_3d(dst + C_::OFF_C, &tm.c, bar, k0t - 16, j0 - 1, l);
-        if (with_old) {
-#pragma unroll
-            for (int q3 = 0; q3 < 3; ++q3) tma_load_3d(dst + C_::OFF_O + q3 * C_::OCOMP, &tm.o[q3], bar, k0t, j0, l);
-        }
+        for (int q3 = 0; q3 < 3; ++q3) tma_load_3d(dst + q3 * C_::UCOMP, &tm.u[q3], bar, k0t - V, j0 - 1, lbase + q);
+        tma_load_3d(dst + C_::OFF_C, &tm.c, bar, k0t - 16, j0 - 1, lbase + q);
     };
-    // `issued` = next plane to hand to the TMA unit.  Nobody blocks to produce: the lane that sees an
-    // `empty[s]` phase complete after its own arrival claims the plane with a CAS and issues it.
+    auto issue_o = [&](int q) {
+        const int s = q % NSO;
+        const uint32_t dst = sb + C_::OFF_O + s * C_::OSTAGE, bar = bar_fullO + s * 8;
+        mbar_expect_tx(bar, C_::TX_O);
+#pragma unroll
+        for (int q3 = 0; q3 < 3; ++q3) tma_load_3d(dst + q3 * C_::OCOMP, &tm.o[q3], bar, k0t, j0, lbase + q);
+    };
+    // claim number c: u_cur plane c (if c < nplanes) and u_old plane c - (NST - NSO) if that plane is one
+    // whose u_new is produced (1 .. nplanes-2).  Every issued load is waited for by some warp before the
+    // block exits -- a TMA still in flight at exit would land in the next block's shared memory.
+    auto issue = [&](int c) {
+        if (c < nplanes) issue_u(c);
+        const int qo = c - (NST - NSO);
+        if (qo >= 1 && qo <= nplanes - 2) issue_o(qo);
+    };
+    const int nclaims = nplanes - 1 + (NST - NSO);
+    // `issued` = next claim.  Nobody blocks to produce: the lane that sees a `done[s]` phase complete
+    // after its own arrival claims with a CAS and issues.
     if (threadIdx.x == 0) {
-        int q = 0;
-        for (; q < NST && q < nplanes; ++q) issue(q);
-        *issued = q;
+        for (int c = 0; c < NST; ++c) issue(c);
+        *issued = NST;
     }
     __syncthreads();
 
@@ -411,7 +427,8 @@ k_step_march(const __grid_constant__ MarchMaps tm, StepArgs<typename A::T> p, Ma
             T t5W = shfl_up1(t5[V - 1]);              // T5(n, k-1) for element 0
             if (lane == 31) t3U = t3R;
             if (lane == 0) { t4W = t4L; t5W = t5L; }  // zero below the k = 0 plane
-            const T *const oC = uC + (C_::OFF_O / SZ) + (r - 1) * TZ + lane * V;   // u_old(n) own vectors
+            mbar_wait(bar_fullO + (it % NSO) * 8, (uint32_t)(((it - 1) / NSO) & 1));   // planes 1, 2, ... use the ring
+            const T *const oC = reinterpret_cast<const T *>(sm + C_::OFF_O + (it % NSO) * C_::OSTAGE) + (r - 1) * TZ + lane * V;   // u_old(n)
             PV ox, oy, oz;
             {   // (5) ux
                 const PV t6S = vec(xb + 2 * XCE + xS), uo = vec(oC);
@@ -472,7 +489,7 @@ k_step_march(const __grid_constant__ MarchMaps tm, StepArgs<typename A::T> p, Ma
             // slowest warp of plane `it`)
             for (;;) {
                 const int q = *reinterpret_cast<volatile int *>(issued);
-                if (q >= nplanes) break;
+                if (q >= nclaims) break;
                 if (!mbar_test(bar_empty + (q % NST) * 8, (uint32_t)((q / NST - 1) & 1))) break;
                 if (atomicCAS(issued, q, q + 1) == q) issue(q);
             }

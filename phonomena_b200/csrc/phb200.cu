@@ -150,7 +150,7 @@ struct phb_ctx {
     // marching kernel: TMA descriptors per [buffer][component], tile plan
     MarchMaps mm[3];           // indexed by the buffer that holds u_cur
     bool maps_ok = false;
-    int mR = 16, mNST = 3, mChunks = 0;
+    int mR = 16, mNST = 4, mChunks = 0;
     IEngine *eng = nullptr;
     std::mutex mu;
 };
@@ -398,10 +398,10 @@ struct Engine : IEngine {
                 const MarchMaps &mp = c->mm[b_cur()];
                 const int ch = plan_chunks(ie - ib);
                 int r = -2;
-                if (c->mR == 16 && c->mNST == 3) r = launch_march_cfg<A, 16, 3>(p, m, mp, ch, c->st);
-                else if (c->mR == 16 && c->mNST == 2) r = launch_march_cfg<A, 16, 2>(p, m, mp, ch, c->st);
-                else if (c->mR == 8 && c->mNST == 3) r = launch_march_cfg<A, 8, 3>(p, m, mp, ch, c->st);
+                if (c->mR == 16 && c->mNST == 4) r = launch_march_cfg<A, 16, 4>(p, m, mp, ch, c->st);
+                else if (c->mR == 16 && c->mNST == 3) r = launch_march_cfg<A, 16, 3>(p, m, mp, ch, c->st);
                 else if (c->mR == 8 && c->mNST == 4) r = launch_march_cfg<A, 8, 4>(p, m, mp, ch, c->st);
+                else if (c->mR == 8 && c->mNST == 3) r = launch_march_cfg<A, 8, 3>(p, m, mp, ch, c->st);
                 if (r == -2) return fail("no marching-kernel instantiation for R=%d NST=%d", c->mR, c->mNST);
                 if (r < 0) return fail("marching kernel needs more shared memory than the device allows (%d classes)", c->ncls);
                 c->launches += r;
@@ -429,7 +429,7 @@ struct Engine : IEngine {
         int best = 1;
         double best_eff = 0;
         for (int ch = 1; ch <= 16 && ch * 8 <= np; ++ch) {
-            if (ch < 16 && (np + ch - 1) / ch > 1024) continue;   // x-spacing table lives in shared memory
+            if (ch < 16 && (np + ch - 1) / ch > 256) continue;    // x-spacing table lives in shared memory
             const long long blocks = tiles * ch, waves = (blocks + slots - 1) / slots;
             const double eff = (double)blocks / (double)(waves * slots) * (1.0 - 1.5 * ch / (double)np);
             if (eff > best_eff + 1e-9) { best_eff = eff; best = ch; }
