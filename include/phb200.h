@@ -98,8 +98,9 @@ int phb_get_material_ids(phb_ctx *ctx, uint8_t *ids);
  * coef = { clx, ctx, cly0, cty0, cly1, cty1, clz, ctz } computed by the host exactly as there. */
 int phb_set_abc(phb_ctx *ctx, const double coef[8]);
 
-/* replaces: wave_fn(tt) (base_solver.py:251,294-312): w[tt] for tt = 0..n-1, evaluated by the
- * host with the reference's own expression. */
+/* replaces: wave_fn(tt) (base_solver.py:251,294-312): the source samples of the NEXT n steps
+ * (w[0] belongs to the step phb_steps_done() reports now), evaluated by the host with the
+ * reference's own expression.  May be called between phb_run calls to stream the samples. */
 int phb_set_source_table(phb_ctx *ctx, const double *w, int64_t n);
 
 /* field transfer (tests, restart, full-field output); which = PHB_CUR | PHB_OLD.
@@ -125,6 +126,12 @@ int phb_steps_done(phb_ctx *ctx, int64_t *tt);
 int phb_launch_count(phb_ctx *ctx, int64_t *n);
 /* name of the stencil kernel variant in use, and device bytes allocated */
 int phb_info(phb_ctx *ctx, char *kernel_name, int32_t len, int64_t *device_bytes);
+
+/* per-kernel timing of the fused stencil launches (the dominant kernel), for the roofline in
+ * bench.py: CUDA event pairs on the launching stream around every stencil launch.
+ * Returns the accumulated milliseconds and launch count since profiling was last (re)enabled;
+ * enable = 1 / 0 switches it on / off and resets the accumulators, enable < 0 only reads. */
+int phb_profile(phb_ctx *ctx, int32_t enable, double *kernel_ms, int64_t *kernel_launches);
 
 /* multi-GPU (one process per GPU): NCCL communicator over the slab chain.
  * replaces: nothing (the reference has no domain decomposition). */

@@ -25,7 +25,7 @@ SYMBOLS = (
     "phb_set_spacing", "phb_set_material_table", "phb_set_material_ids", "phb_gen_material_ids",
     "phb_get_material_ids", "phb_set_abc", "phb_set_source_table", "phb_set_fields", "phb_get_fields",
     "phb_get_stress", "phb_run", "phb_sync", "phb_run_timed", "phb_steps_done", "phb_launch_count",
-    "phb_info", "phb_comm_unique_id", "phb_comm_init", "phb_record_next", "phb_record_release",
+    "phb_info", "phb_profile", "phb_comm_unique_id", "phb_comm_init", "phb_record_next", "phb_record_release",
     "phb_record_frame_doubles",
 )
 
@@ -81,6 +81,7 @@ def load_library(path=None):
     lib.phb_steps_done.argtypes = [vp, C.POINTER(C.c_int64)]
     lib.phb_launch_count.argtypes = [vp, C.POINTER(C.c_int64)]
     lib.phb_info.argtypes = [vp, C.c_char_p, C.c_int32, C.POINTER(C.c_int64)]
+    lib.phb_profile.argtypes = [vp, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     lib.phb_comm_unique_id.argtypes = [C.c_char_p]
     lib.phb_comm_init.argtypes = [vp, C.c_char_p, C.c_int32, C.c_int32]
     lib.phb_record_next.argtypes = [vp, C.POINTER(dp), C.POINTER(C.c_int64), C.c_int32]
@@ -271,6 +272,12 @@ class Engine:
         nbytes = C.c_int64(0)
         _chk(self.lib, self.lib.phb_info(self._ctx, name, 64, C.byref(nbytes)))
         return {"kernel": name.value.decode(), "device_bytes": nbytes.value}
+
+    def profile(self, enable=-1):
+        """(ms, launches) spent in the fused stencil kernel since profiling was (re)enabled."""
+        ms, n = C.c_double(0), C.c_int64(0)
+        _chk(self.lib, self.lib.phb_profile(self._ctx, int(enable), C.byref(ms), C.byref(n)))
+        return ms.value, n.value
 
     # -- multi-GPU ----------------------------------------------------------------------
     def comm_init(self, unique_id, rank, nranks):

@@ -129,8 +129,8 @@ struct phb_ctx {
     void *tab = nullptr;       // class table, ncls x CLS_W
     int ncls = 0;
     void *line_save = nullptr;
-    double *w = nullptr;
-    long long nw = 0;
+    double *w = nullptr;       // source samples for steps w_base .. w_base + nw - 1
+    long long nw = 0, w_base = 0;
     double abc[8] = {};
     bool have_abc = false;
     long long tt = 0;
@@ -151,9 +151,27 @@ struct phb_ctx {
     MarchMaps mm[3];           // indexed by the buffer that holds u_cur
     bool maps_ok = false;
     int mR = 16, mNST = 4, mChunks = 0;
+    // per-kernel timing of the stencil launches (bench roofline): event pairs on the launch stream
+    bool prof = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_ev;
+    size_t prof_used = 0;
+    double prof_ms = 0;
+    long long prof_n = 0;
     IEngine *eng = nullptr;
     std::mutex mu;
 };
+
+static int prof_collect(phb_ctx *c) {
+    for (size_t q = 0; q < c->prof_used; ++q) {
+        float ms = 0;
+        CU(cudaEventSynchronize(c->prof_ev[q].second));
+        CU(cudaEventElapsedTime(&ms, c->prof_ev[q].first, c->prof_ev[q].second));
+        c->prof_ms += ms;
+        c->prof_n++;
+    }
+    c->prof_used = 0;
+    return 0;
+}
 
 static int dmalloc(phb_ctx *c, void **p, size_t bytes, bool zero = true) {
     cudaError_t e = cudaMalloc(p, bytes ? bytes : 1);
@@ -390,6 +408,20 @@ struct Engine : IEngine {
         p.line_save = (c->w && c->cfg.x0 == 0) ? (const T *)c->line_save : nullptr;
         p.i_begin = ib; p.i_end = ie;
         const bool march = use_march();
+        std::pair<cudaEvent_t, cudaEvent_t> *pe = nullptr;
+        if (c->prof) {
+            if (c->prof_used == c->prof_ev.size()) {
+                if (c->prof_ev.size() >= 4096) OK(prof_collect(c));
+                else {
+                    cudaEvent_t a, b;
+                    CU(cudaEventCreate(&a));
+                    CU(cudaEventCreate(&b));
+                    c->prof_ev.push_back({a, b});
+                }
+            }
+            pe = &c->prof_ev[c->prof_used++];
+            CU(cudaEventRecord(pe->first, c->st));
+        }
         if (c->cfg.kernel == PHB_KERNEL_MARCH && !march)
             return fail("kernel=march requested but the marching kernel does not support this grid");
         MatCls<T> m = mat();
@@ -413,6 +445,7 @@ struct Engine : IEngine {
             return 0;
         };
         OK(dispatch(run));
+        if (pe) CU(cudaEventRecord(pe->second, c->st));
         CU(cudaGetLastError());
         return 0;
     }
@@ -523,9 +556,10 @@ struct Engine : IEngine {
         const int x0 = c->cfg.x0, xe = c->cfg.x0 + c->cfg.nxl;
         const bool last = (xe == c->cfg.nx);
         if (c->w && x0 == 0) {
-            if (c->tt >= c->nw) return fail("source table has %lld entries, step %lld requested", c->nw, c->tt);
+            if (c->tt - c->w_base >= c->nw)
+                return fail("source table covers steps %lld..%lld, step %lld requested", c->w_base, c->w_base + c->nw - 1, c->tt);
             k_source<T><<<(c->cfg.ny + 127) / 128, 128, 0, c->st>>>(geo(), (T *)c->buf[b_cur()][2], (T *)c->line_save,
-                                                                   c->w, c->tt);
+                                                                   c->w, c->tt - c->w_base);
             c->launches++;
         }
         if (c->comm && c->nranks > 1) {
@@ -664,9 +698,11 @@ int phb_destroy(phb_ctx *c) {
     for (int b = 0; b < 3; ++b)
         for (int q = 0; q < 3; ++q) cudaFree(c->buf[b][q]);
     for (int a = 0; a < 6; ++a) cudaFree(c->sp[a]);
-    cudaFree(c->tab); cudaFree(c->ids); cudaFree(c->code); cudaFree(c->line_save); cudaFree(c->w);
+    cudaFree(c->tab); cudaFree(c->ids); cudaFree(c->code); cudaFree(c->line_save);
+    if (c->w) cudaFree(c->w);
     if (c->ring) cudaFreeHost(c->ring);
     for (auto &ev : c->slot_ev) cudaEventDestroy(ev);
+    for (auto &pe : c->prof_ev) { cudaEventDestroy(pe.first); cudaEventDestroy(pe.second); }
     if (c->ev_edge) cudaEventDestroy(c->ev_edge);
     if (c->ev_comm) cudaEventDestroy(c->ev_comm);
     if (c->ev_t0) cudaEventDestroy(c->ev_t0);
@@ -800,12 +836,14 @@ int phb_set_abc(phb_ctx *c, const double coef[8]) {
 
 int phb_set_source_table(phb_ctx *c, const double *w, int64_t n) {
     ENTER(c);
-    if (c->w) { cudaFree(c->w); c->w = nullptr; c->nw = 0; }
+    // the previous table may still be read by enqueued steps: stream-ordered free
+    if (c->w) { CU(cudaFreeAsync(c->w, c->st)); c->w = nullptr; c->nw = 0; }
     if (!w || n <= 0) return 0;
-    OK(dmalloc(c, (void **)&c->w, (size_t)n * sizeof(double), false));
+    CU(cudaMallocAsync((void **)&c->w, (size_t)n * sizeof(double), c->st));
     CU(cudaMemcpyAsync(c->w, w, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->st));
     CU(cudaStreamSynchronize(c->st));
     c->nw = n;
+    c->w_base = c->tt;
     return 0;
 }
 
@@ -874,6 +912,19 @@ int phb_info(phb_ctx *c, char *name, int32_t len, int64_t *bytes) {
     if (!c) return fail("null context");
     if (name && len > 0) snprintf(name, len, "%s", c->eng->kernel_name());
     if (bytes) *bytes = c->dev_bytes;
+    return 0;
+}
+
+int phb_profile(phb_ctx *c, int32_t enable, double *kernel_ms, int64_t *kernel_launches) {
+    ENTER(c);
+    OK(prof_collect(c));
+    if (kernel_ms) *kernel_ms = c->prof_ms;
+    if (kernel_launches) *kernel_launches = c->prof_n;
+    if (enable >= 0) {
+        c->prof = enable != 0;
+        c->prof_ms = 0;
+        c->prof_n = 0;
+    }
     return 0;
 }
 

@@ -1,0 +1,326 @@
+"""B200 solver plugin for Phonomena -- drop-in for the solver interface of
+``phonomena/simulation/solvers/solver_*.py`` (reference: ``base_solver.BaseSolver``,
+base_solver.py:172-292, and ``solver_default.Solver``).
+
+Same public surface as the reference plugins:
+
+    s = Solver()                      # zero-arg constructor (common.py:88-91)
+    s.name, s.description, s.cfg, s.file, s.running, s.logger
+    s.init(grid, material, steps)     # base_solver.py:194-222
+    s.run(signals=...)                # base_solver.py:224-280  (status / progress signals)
+    s.cancel()                        # base_solver.py:282-284
+    s.test()                          # base_solver.py:286-292
+
+What changes is what happens inside: the time loop is not NumPy on the host but the sm_100a
+kernels of libphb200.so (include/phb200.h) driven through ctypes; the per-cell material is
+generated on the device from the inclusion list; the surface plane is recorded by the device
+into a pinned host ring and flushed to HDF5 by a writer thread.  No CPU fallback: if the
+library or the GPU is missing, ``init`` raises.
+
+To install into a Phonomena checkout, drop a three-line ``solver_b200.py`` into
+``phonomena/simulation/solvers/``:
+
+    from phonomena_b200.solver_b200 import Solver   # noqa: F401
+"""
+from __future__ import annotations
+
+import copy
+import json
+import logging
+import os
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+from . import _lib, hostmath as hm
+from .h5lite import H5Writer
+
+logger = logging.getLogger(__name__)
+
+# module-level cfg, merged with the base defaults like the reference plugins do
+# (solver_numba.py:8-13,22).  All values are JSON-serialisable (common.saveSettings dumps them).
+cfg = {
+    "precision": "fp64",        # "fp64" | "fp32": storage and arithmetic type on the device
+    "arith": "fast",            # "fast" (<=1e-12 of the reference in fp64) | "exact" (bit-identical, slower)
+    "device": 0,                # CUDA device ordinal (one process per GPU; slabs via torchrun, see slab_from_env)
+    "record": "surface",        # "surface": uz (and ux, uy) at z-index 0 per step | "full": whole fields | "off"
+    "record_every": 1,
+    "chunk_steps": 50,          # steps enqueued per library call (cancel / progress granularity)
+    "kernel": "auto",
+}
+
+
+class _DummySignal:
+    def emit(self, *a, **k):
+        pass
+
+
+class _DummySignals:
+    """Stand-in for gui.worker.WorkerSignals() when run() gets no `signals` (base_solver.py:228-230)."""
+    def __init__(self):
+        self.status = self.progress = self.error = self.finished = _DummySignal()
+
+
+class Writer:
+    """Replaces base_solver.Writer (:72-169): same file schema (App. C), fed from the device ring.
+
+    surface mode: datasets ux (Nx-1,Ny,1,frames), uy (Nx,Ny-1,1,frames), uz (Nx,Ny,1,frames),
+    chunk = one frame, so `u[:, :, 0, t]` of the consumers (h5py2gif.py:24,44; analysis.py:59-66)
+    works unchanged.  full mode: the reference's full 4-D datasets."""
+
+    def __init__(self, path, engine, meta, frames, mode, record_every):
+        self.path, self.e, self.mode, self.frames = path, engine, mode, frames
+        self.h5 = H5Writer(path)
+        self.h5.attrs.update(meta["attrs"])
+        self.h5.attrs["record_every"] = int(record_every)
+        self.h5.attrs["record"] = mode
+        self.h5.create_dataset("density", meta["density"])
+        if meta.get("elasticity") is not None:
+            self.h5.create_dataset("elasticity", meta["elasticity"])
+        nx, ny, nz = engine.nx, engine.ny, engine.nz
+        zext = 1 if mode == "surface" else None
+        self.ds = {
+            "ux": self.h5.create_chunked("ux", (nx - 1, ny, zext or nz, frames)),
+            "uy": self.h5.create_chunked("uy", (nx, ny - 1, zext or nz, frames)),
+            "uz": self.h5.create_chunked("uz", (nx, ny, zext or (nz - 1), frames)),
+        }
+        self.written = 0
+        self.error = None
+        self._stop = threading.Event()
+        self.thread = None
+
+    # surface mode: consumer thread of the pinned ring
+    def start(self):
+        if self.mode != "surface":
+            return
+        self.thread = threading.Thread(target=self._drain, name="phb-writer", daemon=True)
+        self.thread.start()
+
+    def _drain(self):
+        try:
+            while self.written < self.frames:
+                got = self.e.record_next(timeout_ms=200)
+                if got is None:
+                    if self._stop.is_set():
+                        break
+                    continue
+                _tt, views = got
+                for name, a in views.items():
+                    self.h5.write_frame(self.ds[name], self.written, a.reshape(a.shape + (1,)))
+                self.e.record_release()
+                self.written += 1
+        except Exception as exc:       # surfaced by Solver.run
+            self.error = exc
+
+    # full mode: called synchronously by the run loop
+    def put_full(self, fields):
+        for name, a in zip(("ux", "uy", "uz"), fields):
+            self.h5.write_frame(self.ds[name], self.written, a)
+        self.written += 1
+
+    def finish(self, timeout=300.0):
+        if self.thread is not None:
+            self._stop.set()
+            self.thread.join(timeout)
+            if self.thread.is_alive():
+                raise TimeoutError("writer thread did not finish")
+        self.h5.attrs["frames_written"] = int(self.written)
+        self.h5.close()
+        if self.error is not None:
+            raise self.error
+
+
+class Solver:
+    def __init__(self):
+        self.name = "b200"
+        self.description = ("<p>FDTD time stepping on an NVIDIA B200 (sm_100a): fused stress + displacement "
+                            "kernel fed by TMA, absorbing / free-surface boundaries, on-device surface recording. "
+                            "cfg: precision fp64|fp32, arith fast|exact, record surface|full|off.</p>")
+        with tempfile.NamedTemporaryFile() as f:
+            self.file = os.path.realpath(f.name)
+        self.running = threading.Event()
+        self.logger = logger
+        # combine module cfg and the base-class defaults (base_solver.py:190-192)
+        self.cfg = {**cfg, "wave": "ricker", "wave_args": {"f": 100}, "write_mode": "process"}
+        self.engine = None
+        self.writer = None
+        self.stats = {}
+
+    # ------------------------------------------------------------------------------------
+    def init(self, grid, material, steps):
+        """Prepare a run: copies what it needs (the caller's objects are not mutated and may be
+        freed), rebuilds the mesh like the reference does, uploads everything, zeroes the fields."""
+        self._close_engine()
+        c = self.cfg
+        self.t = int(copy.deepcopy(steps))
+        logger.info("Initializing %s with settings: %s", self.name, c)
+
+        # -- mesh: the reference deep-copies the grid and re-runs buildMesh (base_solver.py:199-206).
+        #    Field arrays are not needed here, so only the mesh description is copied.
+        g = _mesh_copy(grid)
+        if hasattr(g, "buildMesh") and getattr(g, "targets", None) is not None and hasattr(g, "spacing_fn"):
+            g.buildMesh()
+        x, y, z = (np.array(a, np.float64) for a in (g.x, g.y, g.z))
+        si = getattr(g, "SI_conversion", 1)
+        fdx, fdy, fdz, sdx, sdy, sdz = hm.spacings(x, y, z, si)
+
+        # -- material: m.update() of the reference works on the material's OWN grid copy
+        #    (material.py:49-50, App. B #11) -> inclusion list and mesh lines come from material.grid
+        mg = getattr(material, "grid", None) or g
+        mx, my, mz = (np.array(a, np.float64) for a in (mg.x, mg.y, mg.z))
+        if (mx.size, my.size, mz.size) != (x.size, y.size, z.size):
+            raise ValueError("material.grid has %s points, solver grid has %s" % ((mx.size, my.size, mz.size), (x.size, y.size, z.size)))
+        prim = {"c": np.array(material.primary["c"], np.float64), "p": float(material.primary["p"]),
+                "name": material.primary.get("name", "primary")}
+        sec = {"c": np.array(material.secondary["c"], np.float64), "p": float(material.secondary["p"]),
+               "name": material.secondary.get("name", "secondary")}
+        msi = getattr(mg, "SI_conversion", 1)
+        mfd = hm.spacings(mx, my, mz, msi)
+        dt = hm.cfl_dt(mfd[0], mfd[1], mfd[2], material.c_max, prim, sec, msi)
+        targets = _targets_array(getattr(mg, "targets", None))
+
+        rec_mode = c["record"] if c.get("write_mode", "off") != "off" else "off"
+        rec_mask = (_lib.REC_UX | _lib.REC_UY | _lib.REC_UZ) if rec_mode == "surface" else 0
+        x0, nxl, rank, nranks = slab_from_env(x.size) if c.get("slabs_from_env") else (0, x.size, 0, 1)
+        e = _lib.Engine(x.size, y.size, z.size, dt, d2=dt ** 2,
+                        dtype={"fp64": "f64", "fp32": "f32"}[c["precision"]], arith=c["arith"],
+                        device=int(c["device"]), x0=x0, nxl=nxl, kernel=c.get("kernel", "auto"),
+                        record_mask=rec_mask, record_every=int(c["record_every"]), ring_slots=32)
+        self.engine = e
+        e.set_spacing(fdx, fdy, fdz, sdx, sdy, sdz)
+        e.set_material_table([prim["c"], sec["c"]], [prim["p"], sec["p"]])
+        e.gen_material_ids(targets, mx, my, mz)
+        ids = e.get_material_ids() if (rec_mode != "off" or x0 == 0) else None
+        corner = int(ids[0, 0, 0]) if (ids is not None and x0 == 0) else 0
+        cm = sec if corner else prim
+        e.set_abc(hm.abc_coefficients(cm["c"], cm["p"], dt, fdx, fdy, fdz, sdx, sdy, sdz))
+        self.dt, self._x0 = dt, x0
+        self._wave, self._wave_args = c["wave"], dict(c["wave_args"])
+
+        self.writer = None
+        if rec_mode != "off":
+            frames = self.t // int(c["record_every"])
+            P = np.where(ids == 1, sec["p"], prim["p"]).astype(np.float64)
+            attrs = {"x": x, "y": y, "z": z,
+                     "sdx": sdx.reshape(-1, 1, 1), "sdy": sdy.reshape(1, -1, 1), "sdz": sdz.reshape(1, 1, -1),
+                     "fdx": fdx.reshape(-1, 1, 1), "fdy": fdy.reshape(1, -1, 1), "fdz": fdz.reshape(1, 1, -1),
+                     "steps": int(self.t), "dt": float(dt), "prim_material": prim["name"], "sec_material": sec["name"],
+                     "solver_cfg": json.dumps(c)}
+            meta = {"attrs": attrs, "density": P, "elasticity": None}
+            if rec_mode == "full" and P.size <= 1 << 22:      # the reference's `elasticity` is 288 B/cell
+                meta["elasticity"] = np.where((ids == 1)[..., None, None], sec["c"], prim["c"])
+            self.writer = Writer(self.file, e, meta, frames, rec_mode, int(c["record_every"]))
+            self.writer.start()
+        self._rec_mode = rec_mode
+
+    # ------------------------------------------------------------------------------------
+    def run(self, *args, **kwargs):
+        signals = kwargs.get("signals") or _DummySignals()
+        if self.engine is None:
+            raise RuntimeError("init() must be called before run()")
+        e, c = self.engine, self.cfg
+        signals.status.emit("Solver starting..")
+        self.running.set()
+        signals.status.emit("Running simulation.")
+        stime = time.time()
+        signals.progress.emit(0)
+        progress = 0
+        chunk = max(1, int(c["chunk_steps"]))
+        every = int(c["record_every"])
+        done = 0
+        l0 = e.launch_count
+        try:
+            while done < self.t:
+                if not self.running.is_set():
+                    self.logger.warning("Simulation cancelled.")
+                    break
+                n = min(chunk, self.t - done)
+                if self._rec_mode == "full":
+                    n = min(n, every - (done % every))
+                # the source samples of this chunk: evaluated on the host with the reference's
+                # expression and copied to the device inside the loop (base_solver.py:251)
+                e.set_source_table(hm.source_table(self._wave, n, self.dt, self._wave_args, start=done))
+                e.run(n)
+                done += n
+                if self._rec_mode == "full" and done % every == 0:
+                    self.writer.put_full(e.get_fields())
+                elif self._rec_mode != "surface":
+                    e.sync()
+                if self.writer is not None and self.writer.error is not None:
+                    raise self.writer.error
+                if progress < 99:
+                    progress = min(99, int((done / self.t) * 100))
+                    signals.progress.emit(progress)
+            e.sync()
+        finally:
+            self.running.clear()
+            if self.writer is not None:
+                self.writer.finish()
+        etime = time.time() - stime
+        cells = e.nx * e.ny * e.nz
+        self.stats = {"steps": done, "seconds": etime, "gcells_per_s": cells * done / etime / 1e9 if etime > 0 else 0.0,
+                      "launches": e.launch_count - l0, "kernel": e.info()["kernel"]}
+        signals.status.emit("Simulation finished in {:.2f}s ({:.2f} Gcell/s).".format(etime, self.stats["gcells_per_s"]))
+        signals.progress.emit(100)
+
+    def cancel(self):
+        if self.running.is_set():
+            self.running.clear()
+
+    def test(self):
+        """base_solver.py:286-292: 10 steps on the reference's TestDefaults grid (needs the reference
+        package on sys.path, as it is when this file sits in its solvers directory)."""
+        from simulation import base_solver     # reference module
+        self.init(grid=base_solver.TestDefaults.g, material=base_solver.TestDefaults.m, steps=10)
+        self.run()
+
+    # -- helpers for tests / scripts -----------------------------------------------------------
+    def fields(self):
+        """(ux, uy, uz) of the current state in the reference's shapes."""
+        return self.engine.get_fields()
+
+    def _close_engine(self):
+        if self.engine is not None:
+            self.engine.close()
+            self.engine = None
+
+    def __del__(self):
+        try:
+            self._close_engine()
+        except Exception:
+            pass
+
+
+# ----------------------------------------------------------------------------------------------
+def _mesh_copy(grid):
+    """Deep copy of the mesh description without the 18 field arrays Grid.update allocates."""
+    skip = {"ux", "uy", "uz", "T1", "T2", "T3", "T4", "T5", "T6"}
+    if not hasattr(grid, "__dict__"):
+        return copy.deepcopy(grid)
+    g = copy.copy(grid)
+    for k, v in list(vars(grid).items()):
+        base = k.split("_")[0]
+        if base in skip and isinstance(v, np.ndarray):
+            setattr(g, k, None)
+        else:
+            setattr(g, k, copy.deepcopy(v))
+    return g
+
+
+def _targets_array(t):
+    """Grid.targets (float32 record array x, y, z, r; grid.py:39) -> (n, 4) float32."""
+    if t is None or len(t) == 0:
+        return np.zeros((0, 4), np.float32)
+    t = np.asarray(t)
+    if t.dtype.names:
+        return np.stack([t["x"], t["y"], t["z"], t["r"]], axis=1).astype(np.float32)
+    return t.astype(np.float32).reshape(-1, 4)
+
+
+def slab_from_env(nx):
+    """x-slab of this process under torchrun (RANK / WORLD_SIZE): (x0, nxl, rank, nranks)."""
+    rank, n = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    x0, nxl = hm.split_slabs(nx, n)[rank]
+    return x0, nxl, rank, n

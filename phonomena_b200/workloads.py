@@ -31,6 +31,7 @@ class Case:
         self.targets = np.asarray(targets, np.float32).reshape(-1, 4)
         self.prim_c, self.prim_p = scaled(primary)
         self.sec_c, self.sec_p = scaled(secondary)
+        self.names = (PROPS[primary]["name"], PROPS[secondary]["name"])
         self.courant, self.wave, self.wave_args = courant, wave, dict(wave_args or {"f": 100})
         self.sp = hm.spacings(self.x, self.y, self.z)
         self.dt = hm.cfl_dt(self.sp[0], self.sp[1], self.sp[2], courant, {"c": self.prim_c, "p": self.prim_p},
@@ -39,6 +40,19 @@ class Case:
     @property
     def shape(self):
         return (self.x.size, self.y.size, self.z.size)
+
+    def as_grid_material(self):
+        """Duck-typed stand-ins for the reference's Grid / Material objects carrying exactly the
+        attributes Solver.init reads (mesh lines, float32 inclusion records, SI_conversion;
+        primary / secondary with the already-scaled 6x6 table, density and name; c_max; grid)."""
+        from types import SimpleNamespace
+        tdt = np.dtype([("x", "f"), ("y", "f"), ("z", "f"), ("r", "f")])      # grid.py:39
+        t = np.array([tuple(r) for r in self.targets], dtype=tdt).reshape(-1)
+        g = SimpleNamespace(x=self.x.copy(), y=self.y.copy(), z=self.z.copy(), targets=t, SI_conversion=1)
+        m = SimpleNamespace(primary={"c": self.prim_c.copy(), "p": self.prim_p, "name": self.names[0]},
+                            secondary={"c": self.sec_c.copy(), "p": self.sec_p, "name": self.names[1]},
+                            c_max=self.courant, grid=g)
+        return g, m
 
     def make_engine(self, steps, x0=0, nxl=None, source_start=0, **kw):
         nx, ny, nz = self.shape

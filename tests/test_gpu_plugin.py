@@ -1,0 +1,118 @@
+"""The plugin (reference interface) end to end on the GPU: Solver.init/run/cancel, signals,
+surface and full-field HDF5 output, compared with the reference's golden outputs."""
+import json
+import threading
+import time
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def fake_from_golden(d):
+    """Grid / Material stand-ins with the attributes Solver.init reads, from a fixture's inputs."""
+    tdt = np.dtype([("x", "f"), ("y", "f"), ("z", "f"), ("r", "f")])
+    t = np.array([tuple(r) for r in d["targets"]], dtype=tdt).reshape(-1)
+    g = SimpleNamespace(x=d["x"].copy(), y=d["y"].copy(), z=d["z"].copy(), targets=t, SI_conversion=1)
+    m = SimpleNamespace(primary={"c": d["prim_c"], "p": d["prim_p"], "name": "P"},
+                        secondary={"c": d["sec_c"], "p": d["sec_p"], "name": "S"}, c_max=d["courant"], grid=g)
+    return g, m
+
+
+class Signals:
+    def __init__(self):
+        self.p, self.s = [], []
+        self.progress = SimpleNamespace(emit=self.p.append)
+        self.status = SimpleNamespace(emit=self.s.append)
+
+
+def make_solver(d, tmp_path, **cfg):
+    from phonomena_b200.solver_b200 import Solver
+    s = Solver()
+    s.cfg.update({"wave": d["wave"], "wave_args": d["wave_args"], "write_mode": "thread", "arith": "exact"})
+    s.cfg.update(cfg)
+    s.file = str(tmp_path / "out.h5")
+    return s
+
+
+@pytest.mark.parametrize("name", ["default_json_1000", "nonuniform_json_200", "partial_depth_dz05"])
+def test_plugin_surface_recording_matches_reference(name, tmp_path):
+    from phonomena_b200.h5lite import H5Reader
+    d = H.load_golden(name)
+    s = make_solver(d, tmp_path, record="surface", chunk_steps=37)
+    g, m = fake_from_golden(d)
+    sig = Signals()
+    s.init(g, m, d["steps"])
+    assert s.dt == d["dt"]
+    s.run(signals=sig)
+    assert sig.p[0] == 0 and sig.p[-1] == 100 and all(isinstance(v, int) for v in sig.p)
+    assert sig.s[0] == "Solver starting.." and "finished" in sig.s[-1]
+    for got, key in zip(s.fields(), ("ux", "uy", "uz")):
+        assert np.array_equal(got, d[key]), key
+    r = H5Reader(s.file)
+    nx, ny, nz = d["ids"].shape
+    assert r.shape("uz") == (nx, ny, 1, d["steps"]) and r.shape("ux") == (nx - 1, ny, 1, d["steps"])
+    assert r.attrs["steps"] == d["steps"] and r.attrs["dt"] == d["dt"] and r.attrs["frames_written"] == d["steps"]
+    assert np.array_equal(r.attrs["x"], d["x"]) and r.attrs["fdx"].shape == (nx - 1, 1, 1)
+    assert json.loads(r.attrs["solver_cfg"])["record"] == "surface"
+    P = np.where(d["ids"] == 1, d["sec_p"], d["prim_p"])
+    assert np.array_equal(r.read("density"), P)
+    # frame t of the file = state after step t+1 (App. B #10), z-index 0
+    for n in (int(v) for v in d["snap_steps"]):
+        assert np.array_equal(r.read("uz", frame=n - 1)[:, :, 0], d["snap_uz_%d" % n]), n
+        assert np.array_equal(r.read("ux", frame=n - 1)[:, :, 0], d["snap_ux_%d" % n]), n
+        assert np.array_equal(r.read("uy", frame=n - 1)[:, :, 0], d["snap_uy_%d" % n]), n
+
+
+def test_plugin_full_field_output_matches_reference_schema(tmp_path):
+    from phonomena_b200.h5lite import H5Reader
+    d = H.load_golden("testdefaults")
+    s = make_solver(d, tmp_path, record="full")
+    g, m = fake_from_golden(d)
+    s.init(g, m, d["steps"])
+    s.run()
+    r = H5Reader(s.file)
+    nx, ny, nz = d["ids"].shape
+    assert r.shape("ux") == (nx - 1, ny, nz, 10) and r.shape("uy") == (nx, ny - 1, nz, 10) and r.shape("uz") == (nx, ny, nz - 1, 10)
+    assert sorted(r.datasets) == ["density", "elasticity", "ux", "uy", "uz"]
+    assert r.read("elasticity").shape == (nx, ny, nz, 6, 6)
+    for key in ("ux", "uy", "uz"):
+        assert np.array_equal(r.read(key, frame=9), d[key]), key
+
+
+def test_plugin_write_mode_off_and_fp32(tmp_path):
+    d = H.load_golden("crystal_48x32x12")
+    s = make_solver(d, tmp_path, write_mode="off", precision="fp32", arith="fast")
+    g, m = fake_from_golden(d)
+    s.init(g, m, d["steps"])
+    s.run()
+    assert H.rel_l2(s.fields(), [d["ux"], d["uy"], d["uz"]]) <= 1e-5
+    assert s.stats["steps"] == d["steps"] and s.stats["launches"] > 0
+
+
+def test_plugin_cancel_from_another_thread(tmp_path):
+    d = H.load_golden("crystal_48x32x12")
+    s = make_solver(d, tmp_path, write_mode="off", chunk_steps=5)
+    g, m = fake_from_golden(d)
+    s.init(g, m, 2_000_000)
+    th = threading.Thread(target=s.run)
+    th.start()
+    time.sleep(0.3)
+    s.cancel()
+    th.join(5)
+    assert not th.is_alive() and 0 < s.stats["steps"] < 2_000_000
+
+
+def test_plugin_does_not_mutate_caller_objects(tmp_path):
+    d = H.load_golden("default_json_1000")
+    s = make_solver(d, tmp_path, write_mode="off")
+    g, m = fake_from_golden(d)
+    x0 = g.x.copy()
+    s.init(g, m, 3)
+    g.x[:] = -1            # the caller may free / reuse its arrays after init()
+    s.run()
+    assert np.array_equal(x0, d["x"]) and s.stats["steps"] == 3

@@ -1,0 +1,90 @@
+"""CPU-only checks: host math equals the oracle bit for bit, slab split, HDF5 writer/reader,
+the C-ABI library loads and exports every symbol include/phb200.h declares, and the product
+fails loudly without a GPU (no CPU fallback)."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from tests import helpers as H
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("name", H.golden_names())
+def test_hostmath_matches_oracle(name):
+    from oracle import fdtd_numpy as onp
+    from phonomena_b200 import hostmath as hm
+    d = H.load_golden(name)
+    o = H.oracle_from_golden(d)
+    sp = hm.spacings(d["x"], d["y"], d["z"])
+    for a, b in zip(sp, (o.fdx, o.fdy, o.fdz, o.sdx, o.sdy, o.sdz)):
+        assert np.array_equal(a, b.reshape(-1))
+    dt = hm.cfl_dt(sp[0], sp[1], sp[2], d["courant"], {"c": d["prim_c"], "p": d["prim_p"]}, {"c": d["sec_c"], "p": d["sec_p"]})
+    assert dt == d["dt"] == o.dt
+    corner = (d["sec_c"], d["sec_p"]) if d["ids"][0, 0, 0] else (d["prim_c"], d["prim_p"])
+    assert hm.abc_coefficients(corner[0], corner[1], dt, *sp) == {k: float(v) for k, v in o.abc_coefficients().items()}
+    w = hm.source_table(d["wave"], 20, dt, d["wave_args"])
+    assert np.array_equal(w, onp.source_table(d["wave"], 20, dt, d["wave_args"]))
+    assert np.array_equal(hm.source_table(d["wave"], 5, dt, d["wave_args"], start=15), w[15:])
+
+
+def test_split_slabs():
+    from phonomena_b200 import hostmath as hm
+    assert hm.split_slabs(4096, 8) == [(512 * r, 512) for r in range(8)]
+    s = hm.split_slabs(1030, 4)
+    assert sum(n for _, n in s) == 1030 and s[0][0] == 0 and all(a[0] + a[1] == b[0] for a, b in zip(s, s[1:]))
+    with pytest.raises(ValueError):
+        hm.split_slabs(10, 4)
+
+
+def test_library_exports_every_declared_symbol():
+    from phonomena_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "phb200.h")).read()
+    declared = set(re.findall(r"\b(phb_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    lib = _lib.load_library()
+    for s in declared:
+        assert hasattr(lib, s), s
+    assert lib.phb_version() == 100
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from phonomena_b200 import _lib
+    with pytest.raises(_lib.PhbError, match="no CPU fallback"):
+        _lib.Engine(8, 8, 8, 1e-5)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "phonomena_b200")
+    for dirpath, _d, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle|#include.*oracle|dlopen.*oracle|CDLL.*oracle", src, re.M), f
+
+
+def test_h5lite_roundtrip_multilevel_btree(tmp_path):
+    from phonomena_b200.h5lite import H5Reader, H5Writer, SIG
+    rng = np.random.default_rng(1)
+    p = str(tmp_path / "t.h5")
+    frames = [rng.standard_normal((7, 5, 1)) for _ in range(5000)]      # > 64*64 chunks -> 3-level B-tree
+    with H5Writer(p) as w:
+        w.attrs.update({"x": np.arange(7.0), "fdx": np.ones((6, 1, 1)), "steps": 5000, "dt": 2.5e-5, "prim_material": "Gallium Arsenide"})
+        P = rng.standard_normal((7, 5, 3))
+        w.create_dataset("density", P)
+        d = w.create_chunked("uz", (7, 5, 1, 5000))
+        for t, f in enumerate(frames):
+            w.write_frame(d, t, f)
+    raw = open(p, "rb").read()
+    assert raw[:8] == SIG and int.from_bytes(raw[40:48], "little") == len(raw)      # signature, EOF address
+    r = H5Reader(p)
+    assert r.attrs["steps"] == 5000 and r.attrs["dt"] == 2.5e-5 and r.attrs["prim_material"] == "Gallium Arsenide"
+    assert r.attrs["fdx"].shape == (6, 1, 1) and r.shape("uz") == (7, 5, 1, 5000)
+    assert np.array_equal(r.read("density"), P)
+    for t in (0, 63, 64, 4095, 4096, 4999):
+        assert np.array_equal(r.read("uz", frame=t), frames[t])

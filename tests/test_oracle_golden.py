@@ -109,3 +109,17 @@ def test_oracle_vs_live_reference_random_fields():
     o.run(4)
     for k in ("ux", "uy", "uz", "ux_old", "uy_old", "uz_old", "T1", "T2", "T3", "T4", "T5", "T6"):
         assert np.array_equal(getattr(o, k), getattr(s.g, k)), k
+
+
+@pytest.mark.parametrize("omp", [False, True])
+@pytest.mark.parametrize("name", H.golden_names())
+def test_c_oracle_bit_exact(name, omp):
+    """The C restatement (oracle/fdtd_c.c) against the reference's golden outputs, bit for bit."""
+    from oracle import fdtd_c
+    d = H.load_golden(name)
+    o = fdtd_c.COracle(d["x"], d["y"], d["z"], d["ids"], [d["prim_c"], d["sec_c"]], [d["prim_p"], d["sec_p"]], d["dt"],
+                       wave=d["wave"], wave_args=d["wave_args"], omp=omp)
+    o.run(d["steps"])
+    for k in ("ux", "uy", "uz", "ux_old", "uy_old", "uz_old", "T1", "T2", "T3", "T4", "T5", "T6"):
+        assert np.array_equal(getattr(o, k), d[k]), (name, k)
+    o.close()
