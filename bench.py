@@ -203,7 +203,9 @@ def run_b200(args):
         return
     peak, peak_src = hbm_peak()
     cells_local = nxl * NY * NZ
-    ach = b_alg(dtype) * cells_local * kn / (kms * 1e-3) / 1e9 if kms > 0 else None    # GB/s of one GPU's kernel
+    # the stencil launches of the K timed steps process cells_local * K cell updates in total (with slabs a step
+    # is an edge launch per neighbour + one interior launch); kms is their summed device time on the slowest rank
+    ach = b_alg(dtype) * cells_local * K / (kms * 1e-3) / 1e9 if kms > 0 else None     # GB/s of one GPU's kernel
     traffic = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
@@ -220,7 +222,7 @@ def run_b200(args):
                    "halo": "NCCL send/recv of 3 planes per direction per step, overlapped with the interior update" if n > 1 else "none"},
         "clocks": clocks, "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None,
-                     "traffic": traffic, "peak_source": peak_src, "kernel": "k_step_march", "kernel_ms_per_launch": kms / kn if kn else None,
+                     "traffic": traffic, "peak_source": peak_src, "kernel": "k_step_march", "kernel_ms_per_step": kms / K if K else None, "kernel_launches_per_step": kn / K if K else None,
                      "algorithmic_bytes_per_cell": b_alg(dtype), "kernel_share_of_step": kms / ms if ms else None},
     }
     if e2e is not None:

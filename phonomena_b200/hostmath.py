@@ -78,3 +78,15 @@ def split_slabs(nx, nparts, min_planes=4):
         out.append((x0, n))
         x0 += n
     return out
+
+
+def halo_plan(rank, nranks, nxl):
+    """Halo exchange of one x-slab with its neighbours, as (peer, local plane sent, local plane
+    received into); local plane l = i - x0 + 1, so 1 and nxl are the first / last owned planes and
+    0 / nxl + 1 the ghosts (phb200.cu exchange(): same pairs, three components each)."""
+    plan = []
+    if rank > 0:
+        plan.append((rank - 1, 1, 0))
+    if rank < nranks - 1:
+        plan.append((rank + 1, nxl, nxl + 1))
+    return plan

@@ -1,0 +1,53 @@
+"""Multi-GPU parity check, launched by torchrun (one process per GPU):
+every rank steps its x-slab with NCCL halo exchange; the slabs must be BIT-IDENTICAL to the
+same planes of a single-GPU run (same kernel, same arithmetic order)."""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from phonomena_b200 import _lib, hostmath as hm
+from phonomena_b200.workloads import crystal_case
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    nx, ny, nz = [int(v) for v in os.environ.get("PHB_MC_GRID", "96,72,80").split(",")]
+    steps = int(os.environ.get("PHB_MC_STEPS", "40"))
+    ok = True
+    for dtype, arith, kernel in (("f64", "fast", "march"), ("f64", "exact", "march"), ("f32", "fast", "march"), ("f64", "fast", "naive")):
+        case = crystal_case(nx, ny, nz)
+        x0, nxl = hm.split_slabs(nx, world)[rank]
+        e = case.make_engine(steps=steps, x0=x0, nxl=nxl, dtype=dtype, arith=arith, device=local, kernel=kernel)
+        uid = [_lib.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        e.comm_init(uid[0], rank, world)
+        e.run(steps)
+        e.sync()
+        mine = e.get_fields()
+        e.close()
+        # single-GPU run of the whole grid on every rank's own device, compared on the owned planes
+        f = case.make_engine(steps=steps, dtype=dtype, arith=arith, device=local, kernel=kernel)
+        f.run(steps)
+        full = f.get_fields()
+        f.close()
+        same = all(np.array_equal(a, b[x0:x0 + a.shape[0]]) for a, b in zip(mine, full))
+        nrm = float(sum(np.sum(a.astype(np.float64) ** 2) for a in mine))
+        t = torch.tensor([1.0 if same else 0.0, nrm], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        if rank == 0:
+            print(json.dumps({"dtype": dtype, "arith": arith, "kernel": kernel, "ranks_identical": int(t[0]), "world": world,
+                              "energy": float(t[1])}), flush=True)
+        ok = ok and int(t[0]) == world and float(t[1]) > 0
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
