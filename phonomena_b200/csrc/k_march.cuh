@@ -91,11 +91,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "{\n"
         ".reg .pred p;\n"
         "W_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
         "@p bra D_%=;\n"
         "bra W_%=;\n"
         "D_%=:\n"
-        "}\n" ::"r"(bar), "r"(parity) : "memory");
+        "}\n" ::"r"(bar), "r"(parity), "r"(0x989680u) : "memory");   // suspend-time hint: sleep in HW, do not spin
 }
 __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
     uint32_t ok;
@@ -292,8 +292,11 @@ k_step_march(const __grid_constant__ MarchMaps tm, StepArgs<typename A::T> p, Ma
     // ---- loop-invariant per-thread quantities (kept few: everything else is re-read from smem) ----
     const bool in_box = (j >= 0 && j < g.ny && kb < g.nzp);      // global vector stores allowed
     const bool row_out = (r >= 1 && r <= R - 2) && (j < g.ny);    // this WARP produces u_new (warp-uniform)
-    const bool haveL = (lane == 0) && (k0t >= 1) && (j >= 0 && j < g.ny);           // halo column kL = k0t-1
-    const bool haveR = (lane == 31) && (k0t + TZ <= g.nz - 1) && (j >= 0 && j < g.ny);   // halo column kR
+    // halo-row warps only produce what their one neighbour reads: the bottom row (r = 0) T4 and T6,
+    // the top row (r = R-1) T2; everything else they would compute is dead (warp-uniform branches)
+    const bool need_shear = (r != R - 1), need_normal = (r != 0);
+    const bool haveL = (lane == 0) && (k0t >= 1) && (j >= 0 && j < g.ny) && row_out;   // halo column kL = k0t-1
+    const bool haveR = (lane == 31) && (k0t + TZ <= g.nz - 1) && (j >= 0 && j < g.ny) && row_out;   // halo column kR
     const int eo = r * ROWE + (lane + 1) * V;          // own vector inside a u_cur component tile (elements)
     const int eS = (r >= 1) ? -ROWE : 0, eN = (r <= R - 2) ? ROWE : 0;            // neighbour rows (clamped)
     const int xo = r * (TZ) + lane * V;                // own vector inside an exchange component tile
@@ -306,8 +309,9 @@ k_step_march(const __grid_constant__ MarchMaps tm, StepArgs<typename A::T> p, Ma
     T t1c[V], t2c[V], t3c[V];    // T1..T3(n)
     T t5m[V], t6m[V];            // T5(n-1), T6(n-1)
     T t3R = (T)0;                // T3(n, j, kR) for lane 31
+    const T *rowc[V];            // class rows (coefficients) of this thread's cells at plane n
 #pragma unroll
-    for (int e = 0; e < V; ++e) t1c[e] = t2c[e] = t3c[e] = t5m[e] = t6m[e] = (T)0;
+    for (int e = 0; e < V; ++e) { t1c[e] = t2c[e] = t3c[e] = t5m[e] = t6m[e] = (T)0; rowc[e] = stab; }
 
     T *pnx = p.nw.ux + ((long long)lbase * g.ps + (long long)j * g.nzp + kb);   // (plane n, j, kb) of u_new
     const long long dyz = (long long)(p.nw.uy - p.nw.ux), dzz_ = (long long)(p.nw.uz - p.nw.ux);
@@ -337,8 +341,14 @@ k_step_march(const __grid_constant__ MarchMaps tm, StepArgs<typename A::T> p, Ma
         T t4[V], t5[V], t6[V];
         T t4L = (T)0, t5L = (T)0;
         const PV uxc = vec(uC + eo), uyc = vec(uC + UCE + eo), uzc = vec(uC + 2 * UCE + eo);
-        const CW cwc = *reinterpret_cast<const CW *>(sm + sCi * C_::STAGE + C_::OFF_C + r * C_::CB + 16 + lane * V);
-        {
+#pragma unroll
+        for (int e = 0; e < V; ++e) t4[e] = t5[e] = t6[e] = (T)0;
+        if (it == 0 || !need_normal) {   // (the bottom halo row never runs the normal-stress phase that carries the rows)
+            const CW cwc = *reinterpret_cast<const CW *>(sm + sCi * C_::STAGE + C_::OFF_C + r * C_::CB + 16 + lane * V);
+#pragma unroll
+            for (int e = 0; e < V; ++e) rowc[e] = stab + (int)((cwc >> (8 * e)) & 255u) * CLS_W;
+        }
+        if (need_shear) {
             const PV uyn = vec(uN + UCE + eo), uzn = vec(uN + 2 * UCE + eo);
             const PV uzN = vec(uC + 2 * UCE + eo + eN), uxN = vec(uC + eo + eN);     // uz(n, j+1), ux(n, j+1)
             T uyE = shfl_dn1(uyc.v[0]), uxE = shfl_dn1(uxc.v[0]);                    // uy(n, k+1), ux(n, k+1)
@@ -348,7 +358,7 @@ k_step_march(const __grid_constant__ MarchMaps tm, StepArgs<typename A::T> p, Ma
             for (int e = 0; e < V; ++e) {
                 const T uye = (e == V - 1) ? uyE : uyc.v[e < V - 1 ? e + 1 : e];
                 const T uxe = (e == V - 1) ? uxE : uxc.v[e < V - 1 ? e + 1 : e];
-                const T *c = stab + (int)((cwc >> (8 * e)) & 255u) * CLS_W;
+                const T *c = rowc[e];
                 const bool k0 = (e == 0) && k0c;
                 const T shb = (e == 0) ? shb0 : sfx_n;
                 t4[e] = shear<A>(c[CLS_C44], A::sub(uye, uyc.v[e]), k0 ? g.fdy0 : zf.v[e],
@@ -385,7 +395,10 @@ k_step_march(const __grid_constant__ MarchMaps tm, StepArgs<typename A::T> p, Ma
         // (3) normal stresses at plane n + 1 (overlaps the neighbours' publishing)
         T t1n[V], t2n[V], t3n[V];
         T t3Rn = (T)0;
-        {
+        const T *rown[V];
+#pragma unroll
+        for (int e = 0; e < V; ++e) { t1n[e] = t2n[e] = t3n[e] = (T)0; rown[e] = stab; }
+        if (need_normal) {
             const PV uxn = vec(uN + eo), uyn = vec(uN + UCE + eo), uzn = vec(uN + 2 * UCE + eo);
             const PV uyS = vec(uN + UCE + eo + eS);                              // uy(n+1, j-1)
             T uzW0 = shfl_up1(uzn.v[V - 1]);                                     // uz(n+1, k-1) for element 0
@@ -398,7 +411,7 @@ k_step_march(const __grid_constant__ MarchMaps tm, StepArgs<typename A::T> p, Ma
                 const T dyy = A::sub(uyn.v[e], uyS.v[e]);
                 const T dzz = A::sub(uzn.v[e], (e == 0) ? uzW0 : uzn.v[e > 0 ? e - 1 : 0]);
                 const T sx = k0 ? g.sdx0 : ssx_n, sy = k0 ? g.sdy0 : ssy;
-                const T *c = stab + (int)((cwn >> (8 * e)) & 255u) * CLS_W;
+                const T *c = rown[e] = stab + (int)((cwn >> (8 * e)) & 255u) * CLS_W;
                 t1n[e] = normal_row<A>(c + 0, dxx, dyy, dzz, sx, sy, zs.v[e]);
                 t2n[e] = normal_row<A>(c + 3, dxx, dyy, dzz, sx, sy, zs.v[e]);
                 t3n[e] = normal_row<A>(c + 6, dxx, dyy, dzz, sx, sy, zs.v[e]);
@@ -435,7 +448,7 @@ k_step_march(const __grid_constant__ MarchMaps tm, StepArgs<typename A::T> p, Ma
 #pragma unroll
                 for (int e = 0; e < V; ++e) {
                     const bool k0 = (e == 0) && k0c;
-                    const T *c = stab + (int)((cwc >> (8 * e)) & 255u) * CLS_W;
+                    const T *c = rowc[e];
                     const T t5w = (e == 0) ? t5W : t5[e > 0 ? e - 1 : 0];
                     const T acc = A::add(A::add(A::scl(A::sub(t1n[e], t1c[e]), k0 ? g.fdx0 : sfx_n),
                                                 A::scl(A::sub(t6[e], t6S.v[e]), k0 ? g.sdy0 : ssy)),
@@ -448,7 +461,7 @@ k_step_march(const __grid_constant__ MarchMaps tm, StepArgs<typename A::T> p, Ma
 #pragma unroll
                 for (int e = 0; e < V; ++e) {
                     const bool k0 = (e == 0) && k0c;
-                    const T *c = stab + (int)((cwc >> (8 * e)) & 255u) * CLS_W;
+                    const T *c = rowc[e];
                     const T t4w = (e == 0) ? t4W : t4[e > 0 ? e - 1 : 0];
                     const T acc = A::add(A::add(A::scl(A::sub(t6[e], t6m[e]), k0 ? g.sdx0 : ssx_m),
                                                 A::scl(A::sub(t2N.v[e], t2c[e]), k0 ? g.fdy0 : sfy)),
@@ -461,7 +474,7 @@ k_step_march(const __grid_constant__ MarchMaps tm, StepArgs<typename A::T> p, Ma
 #pragma unroll
                 for (int e = 0; e < V; ++e) {
                     const bool k0 = (e == 0) && k0c;
-                    const T *c = stab + (int)((cwc >> (8 * e)) & 255u) * CLS_W;
+                    const T *c = rowc[e];
                     const T t3u = (e == V - 1) ? t3U : t3c[e < V - 1 ? e + 1 : e];
                     const T acc = A::add(A::add(A::scl(A::sub(t5[e], t5m[e]), k0 ? g.sdx0 : ssx_m),
                                                 A::scl(A::sub(t4[e], t4S.v[e]), k0 ? g.sdy0 : ssy)),
@@ -501,7 +514,7 @@ k_step_march(const __grid_constant__ MarchMaps tm, StepArgs<typename A::T> p, Ma
         sCi = sNi;
         if (++sNi == NST) { sNi = 0; phN ^= 1u; }
 #pragma unroll
-        for (int e = 0; e < V; ++e) { t1c[e] = t1n[e]; t2c[e] = t2n[e]; t3c[e] = t3n[e]; t5m[e] = t5[e]; t6m[e] = t6[e]; }
+        for (int e = 0; e < V; ++e) { t1c[e] = t1n[e]; t2c[e] = t2n[e]; t3c[e] = t3n[e]; t5m[e] = t5[e]; t6m[e] = t6[e]; rowc[e] = rown[e]; }
     }
 }
 
