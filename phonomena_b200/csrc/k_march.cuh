@@ -47,7 +47,7 @@ template <class T, int R, int NST>
 struct MarchCfg {
     static constexpr int V = VecOf<T>::V;
     static constexpr int SZ = (int)sizeof(T);
-    static constexpr int NSO = 2;                     // depth of the u_old ring
+    static constexpr int NSO = (NST >= 4) ? 2 : NST;   // depth of the u_old ring (4+2 or 3+3 stages fit 227 KB)
     static constexpr int TZ = 32 * V;                 // cells per tile row
     static constexpr int TY = R - 2;                  // output rows per tile
     static constexpr int ROWB = 34 * 16;              // u_cur ring row: 34 vectors of 16 B (halo vector each side)
@@ -196,7 +196,7 @@ k_step_march(const __grid_constant__ MarchMaps tm, StepArgs<typename A::T> p, Ma
     using C_ = MarchCfg<T, R, NST>;
     constexpr int V = C_::V, SZ = C_::SZ, TZ = C_::TZ;
     constexpr int UCE = C_::UCOMP / SZ, OCE = C_::OCOMP / SZ, XCE = C_::XCOMP / SZ;   // component strides in elements
-    static_assert(NST > C_::NSO, "u_cur ring must be deeper than the u_old ring");
+    static_assert(NST >= C_::NSO, "u_cur ring must be at least as deep as the u_old ring");
     constexpr int ROWE = C_::ROWB / SZ;
     using PV = Pack<T, V>;
     using CW = typename std::conditional<V == 4, uint32_t, uint16_t>::type;            // V class bytes
@@ -249,7 +249,7 @@ k_step_march(const __grid_constant__ MarchMaps tm, StepArgs<typename A::T> p, Ma
         if (threadIdx.x == 0) {
             for (int s = 0; s < NST; ++s) { mbar_init(bar_full + s * 8, 1); mbar_init(bar_empty + s * 8, R); }
             for (int s = 0; s < NSO; ++s) mbar_init(bar_fullO + s * 8, 1);
-            for (int q = 0; q < 2 * R; ++q) mbar_init(bar_pub + q * 8, 1);
+            for (int q = 0; q < 2 * R; ++q) mbar_init(bar_pub + q * 8, (q / 2 == 0 || q / 2 == R - 1) ? 1 : 2);   // arrivals = neighbours
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
     }
@@ -313,8 +313,9 @@ k_step_march(const __grid_constant__ MarchMaps tm, StepArgs<typename A::T> p, Ma
 #pragma unroll
     for (int e = 0; e < V; ++e) { t1c[e] = t2c[e] = t3c[e] = t5m[e] = t6m[e] = (T)0; rowc[e] = stab; }
 
-    T *pnx = p.nw.ux + ((long long)lbase * g.ps + (long long)j * g.nzp + kb);   // (plane n, j, kb) of u_new
-    const long long dyz = (long long)(p.nw.uy - p.nw.ux), dzz_ = (long long)(p.nw.uz - p.nw.ux);
+    // element offset of (plane n, j, kb) in a displacement array (the host guarantees it fits 31 bits)
+    int off = (int)((long long)lbase * g.ps + (long long)j * g.nzp + kb);
+    const int dps = (int)g.ps;
 
     mbar_wait(bar_full, 0);                           // plane q = 0 (n = ia - 1)
     int sCi = 0, sNi = 1 % NST;                       // stage indices of plane n and n + 1
@@ -390,7 +391,9 @@ k_step_march(const __grid_constant__ MarchMaps tm, StepArgs<typename A::T> p, Ma
             *reinterpret_cast<PV *>(xb + 2 * XCE) = c;
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(pubO + (it & 1) * 8);
+        // tell both neighbours (arrive on THEIR barrier): each warp then waits on one barrier only
+        if (lane == 0 && r >= 1) mbar_arrive(pubO - 16 + (it & 1) * 8);
+        if (lane == 1 && r <= R - 2) mbar_arrive(pubO + 16 + (it & 1) * 8);
 
         // (3) normal stresses at plane n + 1 (overlaps the neighbours' publishing)
         T t1n[V], t2n[V], t3n[V];
@@ -427,11 +430,7 @@ k_step_march(const __grid_constant__ MarchMaps tm, StepArgs<typename A::T> p, Ma
         }
 
         // wait for both neighbours' plane-n stresses (also bounds the drift between warps)
-        {
-            const uint32_t ph = (it >> 1) & 1;
-            if (r >= 1) mbar_wait(pubO - 16 + (it & 1) * 8, ph);
-            if (r <= R - 2) mbar_wait(pubO + 16 + (it & 1) * 8, ph);
-        }
+        mbar_wait(pubO + (it & 1) * 8, (it >> 1) & 1);
 
         if (emit && row_out) {
             // (4) z-neighbour stresses
@@ -489,9 +488,9 @@ k_step_march(const __grid_constant__ MarchMaps tm, StepArgs<typename A::T> p, Ma
                 if (k0c && p.line_save) oz.v[0] = p.line_save[j];
             }
             if (in_box) {
-                *reinterpret_cast<PV *>(pnx) = ox;
-                *reinterpret_cast<PV *>(pnx + dyz) = oy;
-                *reinterpret_cast<PV *>(pnx + dzz_) = oz;
+                *reinterpret_cast<PV *>(p.nw.ux + off) = ox;
+                *reinterpret_cast<PV *>(p.nw.uy + off) = oy;
+                *reinterpret_cast<PV *>(p.nw.uz + off) = oz;
             }
         }
         // every read this warp makes of the stage holding plane n is done
@@ -510,7 +509,7 @@ k_step_march(const __grid_constant__ MarchMaps tm, StepArgs<typename A::T> p, Ma
 
         // (8) rotate
         t3R = t3Rn;
-        pnx += g.ps;
+        off += dps;
         sCi = sNi;
         if (++sNi == NST) { sNi = 0; phN ^= 1u; }
 #pragma unroll

@@ -451,9 +451,11 @@ struct Engine : IEngine {
     }
     bool use_march() const {
         if (c->cfg.kernel == PHB_KERNEL_NAIVE) return false;
-        return c->maps_ok;
+        return c->maps_ok && march_fits();
     }
     // x-chunks per launch: fill whole waves of (148 SMs x resident blocks) with the (y,z) tiles
+    // the marching kernel addresses elements with 31-bit offsets
+    bool march_fits() const { return (long long)(c->cfg.nxl + 2) * c->ps < (1LL << 31); }
     int plan_chunks(int np) const {
         if (c->mChunks > 0) return c->mChunks;
         const int V = VecOf<T>::V, TZ = 32 * V, TY = c->mR - 2;
