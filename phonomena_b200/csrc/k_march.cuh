@@ -37,6 +37,10 @@
 
 #include "k_naive.cuh"
 
+#ifndef PHB_UNROLL
+#define PHB_UNROLL 2
+#endif
+
 namespace phb {
 
 template <class T> struct VecOf;
@@ -321,7 +325,8 @@ k_step_march(const __grid_constant__ MarchMaps tm, StepArgs<typename A::T> p, Ma
     int sCi = 0, sNi = 1 % NST;                       // stage indices of plane n and n + 1
     uint32_t phN = 0;                                 // phase parity of full[sNi] for plane n + 1
 
-#pragma unroll 1
+    constexpr int kUnroll = PHB_UNROLL;
+#pragma unroll kUnroll
     for (int it = 0; it + 1 < nplanes; ++it) {
         const int n = ia - 1 + it;                    // plane being completed; n + 1 is the newest
         const bool emit = (it >= 1);                  // it = 0 only primes the carried stresses
@@ -415,9 +420,16 @@ k_step_march(const __grid_constant__ MarchMaps tm, StepArgs<typename A::T> p, Ma
                 const T dzz = A::sub(uzn.v[e], (e == 0) ? uzW0 : uzn.v[e > 0 ? e - 1 : 0]);
                 const T sx = k0 ? g.sdx0 : ssx_n, sy = k0 ? g.sdy0 : ssy;
                 const T *c = rown[e] = stab + (int)((cwn >> (8 * e)) & 255u) * CLS_W;
-                t1n[e] = normal_row<A>(c + 0, dxx, dyy, dzz, sx, sy, zs.v[e]);
-                t2n[e] = normal_row<A>(c + 3, dxx, dyy, dzz, sx, sy, zs.v[e]);
-                t3n[e] = normal_row<A>(c + 6, dxx, dyy, dzz, sx, sy, zs.v[e]);
+                if constexpr (A::EXACT) {
+                    t1n[e] = normal_row<A>(c + 0, dxx, dyy, dzz, sx, sy, zs.v[e]);
+                    t2n[e] = normal_row<A>(c + 3, dxx, dyy, dzz, sx, sy, zs.v[e]);
+                    t3n[e] = normal_row<A>(c + 6, dxx, dyy, dzz, sx, sy, zs.v[e]);
+                } else {   // FAST: the three rows share the scaled strains (spacing tables hold reciprocals)
+                    const T ex = dxx * sx, ey = dyy * sy, ez = dzz * zs.v[e];
+                    t1n[e] = c[0] * ex + c[1] * ey + c[2] * ez;
+                    t2n[e] = c[3] * ex + c[4] * ey + c[5] * ez;
+                    t3n[e] = c[6] * ex + c[7] * ey + c[8] * ez;
+                }
             }
             if (haveR) {   // T3(n+1, j, kR) for the next plane's uz update of the last element (never k = 0)
                 const T *c = stab + (int)sm[sNi * C_::STAGE + C_::OFF_C + r * C_::CB + 16 + TZ] * CLS_W;
