@@ -284,7 +284,7 @@ k_step_march(const __grid_constant__ MarchMaps tm, StepArgs<typename A::T> p, Ma
         const int qo = c - (NST - NSO);
         if (qo >= 1 && qo <= nplanes - 2) issue_o(qo);
     };
-    const int nclaims = nplanes - 1 + (NST - NSO);
+    const int nclaims = max(nplanes, nplanes - 1 + (NST - NSO));   // last u_cur plane / last u_old plane
     // `issued` = next claim.  Nobody blocks to produce: the lane that sees a `done[s]` phase complete
     // after its own arrival claims with a CAS and issues.
     if (threadIdx.x == 0) {
