@@ -212,8 +212,9 @@ k_step_march(const __grid_constant__ MarchMaps tm, StepArgs<typename A::T> p, Ma
     const int lane = threadIdx.x & 31, r = threadIdx.x >> 5;
     const int k0t = blockIdx.x * TZ;                 // first cell of the tile row
     const int j0 = blockIdx.y * C_::TY;              // first output row
-    const int ia = p.i_begin + blockIdx.z * chunk;   // planes [ia, ib)
-    const int ib = min(ia + chunk, p.i_end);
+    // planes [ia, ib): x-chunk blockIdx.z of [i_begin, i_end), or (edge launch) the single planes i_begin / edge_b
+    const int ia = (p.edge_b >= 0) ? (blockIdx.z == 0 ? p.i_begin : p.edge_b) : p.i_begin + blockIdx.z * chunk;
+    const int ib = (p.edge_b >= 0) ? ia + 1 : min(ia + chunk, p.i_end);
     if (ia >= ib) return;
     const int j = j0 - 1 + r;
     const int kb = k0t + lane * V;                   // first cell of this lane
@@ -593,7 +594,7 @@ inline int launch_march_cfg(const StepArgs<typename A::T> &p, const MatCls<typen
         }
         attr_bytes = smem;
     }
-    dim3 grid((p.g.nzp + C_::TZ - 1) / C_::TZ, (p.g.ny + C_::TY - 1) / C_::TY, (np + chunk - 1) / chunk);
+    dim3 grid((p.g.nzp + C_::TZ - 1) / C_::TZ, (p.g.ny + C_::TY - 1) / C_::TY, p.edge_b >= 0 ? 2 : (np + chunk - 1) / chunk);
     kern<<<grid, R * 32, smem, st>>>(maps, p, m, chunk);
     return 1;
 }

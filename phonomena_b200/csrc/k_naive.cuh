@@ -13,6 +13,7 @@ struct StepArgs {
     Fld<T> cur, old, nw;
     const T *line_save;   // pre-source uz(0, j, 0) of `cur` (App. B #9), or nullptr
     int i_begin, i_end;   // global planes to update: [i_begin, i_end)
+    int edge_b;           // >= 0: second single plane of an 'edge launch' (planes i_begin and edge_b, one chunk each)
 };
 
 // u_new for one cell from generic stress evaluations.  Writes only entries the reference's

@@ -141,7 +141,10 @@ struct phb_ctx {
     int rank = 0, nranks = 1;
     // recorder
     double *ring = nullptr;    // pinned host, mapped
-    double *ring_dev = nullptr;
+    double *ring_dev = nullptr;   // device staging ring (same slots): the gather kernel runs at HBM speed,
+                                  // the D2H copy to the pinned ring runs on its own stream behind it
+    cudaStream_t rst = nullptr;
+    std::vector<cudaEvent_t> stage_ev;
     long long frame_doubles = 0;
     int slots = 0;
     std::vector<cudaEvent_t> slot_ev;
@@ -400,9 +403,11 @@ struct Engine : IEngine {
     }
 
     // ---- one time step -----------------------------------------------------------------------
-    int physics(int ib, int ie) {
+    // edge_b >= 0: edge launch of the two single planes ib and edge_b (marching kernel only)
+    int physics(int ib, int ie, int edge_b = -1) {
         if (ie <= ib) return 0;
         StepArgs<T> p;
+        p.edge_b = edge_b;
         p.g = geo();
         p.cur = fld(b_cur()); p.old = fld(b_old()); p.nw = fld(b_new());
         p.line_save = (c->w && c->cfg.x0 == 0) ? (const T *)c->line_save : nullptr;
@@ -568,8 +573,15 @@ struct Engine : IEngine {
             // edge planes first so that the exchange overlaps the interior update
             const bool hasL = c->rank > 0, hasR = c->rank < c->nranks - 1;
             int ib = x0, ie = xe;
-            if (hasL) { OK(physics(x0, x0 + 1)); OK(abc_yz(x0, x0 + 1)); ib = x0 + 1; }
-            if (hasR) { OK(physics(xe - 1, xe)); OK(abc_yz(xe - 1, xe)); ie = xe - 1; }
+            if (hasL && hasR && use_march()) {
+                OK(physics(x0, x0 + 1, xe - 1));      // both edge planes in one launch
+                OK(abc_yz(x0, x0 + 1));
+                OK(abc_yz(xe - 1, xe));
+                ib = x0 + 1; ie = xe - 1;
+            } else {
+                if (hasL) { OK(physics(x0, x0 + 1)); OK(abc_yz(x0, x0 + 1)); ib = x0 + 1; }
+                if (hasR) { OK(physics(xe - 1, xe)); OK(abc_yz(xe - 1, xe)); ie = xe - 1; }
+            }
             CU(cudaEventRecord(c->ev_edge, c->st));
             CU(cudaStreamWaitEvent(c->cst, c->ev_edge, 0));
             OK(exchange());
@@ -609,7 +621,11 @@ static int record_frame(phb_ctx *c) {
     }
     c->launches++;
     CU(cudaGetLastError());
-    CU(cudaEventRecord(c->slot_ev[s], c->st));
+    CU(cudaEventRecord(c->stage_ev[s], c->st));
+    CU(cudaStreamWaitEvent(c->rst, c->stage_ev[s], 0));
+    CU(cudaMemcpyAsync(c->ring + (long long)s * c->frame_doubles, slot, (size_t)c->frame_doubles * sizeof(double),
+                       cudaMemcpyDeviceToHost, c->rst));
+    CU(cudaEventRecord(c->slot_ev[s], c->rst));
     c->slot_tt[s] = c->tt - 1;
     c->produced.fetch_add(1);
     return 0;
@@ -679,10 +695,13 @@ int phb_create(const phb_cfg *cfg, phb_ctx **out) {
         if (cfg->record_mask & PHB_REC_UZ) fd += (long long)cfg->nxl * cfg->ny;
         c->frame_doubles = fd;
         c->slots = cfg->ring_slots > 0 ? cfg->ring_slots : 16;
-        if (cudaHostAlloc((void **)&c->ring, (size_t)c->slots * fd * sizeof(double), cudaHostAllocMapped) != cudaSuccess)
+        if (cudaHostAlloc((void **)&c->ring, (size_t)c->slots * fd * sizeof(double), cudaHostAllocDefault) != cudaSuccess)
             return cleanup(fail("cudaHostAlloc of the %d-slot recorder ring failed", c->slots));
-        if (cudaHostGetDevicePointer((void **)&c->ring_dev, c->ring, 0) != cudaSuccess) return cleanup(fail("cudaHostGetDevicePointer failed"));
+        if (dmalloc(c, (void **)&c->ring_dev, (size_t)c->slots * fd * sizeof(double), false)) return cleanup(1);
+        if (cudaStreamCreateWithFlags(&c->rst, cudaStreamNonBlocking) != cudaSuccess) return cleanup(fail("stream create failed"));
         c->slot_ev.resize(c->slots);
+        c->stage_ev.resize(c->slots);
+        for (auto &ev : c->stage_ev) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
         c->slot_tt.assign(c->slots, -1);
         for (auto &ev : c->slot_ev) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     }
@@ -704,6 +723,9 @@ int phb_destroy(phb_ctx *c) {
     if (c->w) cudaFree(c->w);
     if (c->ring) cudaFreeHost(c->ring);
     for (auto &ev : c->slot_ev) cudaEventDestroy(ev);
+    for (auto &ev : c->stage_ev) cudaEventDestroy(ev);
+    if (c->rst) { cudaStreamSynchronize(c->rst); cudaStreamDestroy(c->rst); }
+    cudaFree(c->ring_dev);
     for (auto &pe : c->prof_ev) { cudaEventDestroy(pe.first); cudaEventDestroy(pe.second); }
     if (c->ev_edge) cudaEventDestroy(c->ev_edge);
     if (c->ev_comm) cudaEventDestroy(c->ev_comm);
@@ -886,6 +908,7 @@ int phb_sync(phb_ctx *c) {
     ENTER(c);
     CU(cudaStreamSynchronize(c->st));
     CU(cudaStreamSynchronize(c->cst));
+    if (c->rst) CU(cudaStreamSynchronize(c->rst));
     return 0;
 }
 int phb_run_timed(phb_ctx *c, int64_t nsteps, float *ms) {
