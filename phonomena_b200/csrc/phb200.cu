@@ -468,7 +468,10 @@ struct Engine : IEngine {
         const long long slots = 148LL * (c->mR <= 8 ? 2 : 1);
         int best = 1;
         double best_eff = 0;
-        for (int ch = 1; ch <= 16 && ch * 8 <= np; ++ch) {
+        // with a halo exchange in flight NCCL CTAs hold a few SMs when the interior launch starts: finer chunks let
+        // the block scheduler rebalance instead of ending with a straggler wave (measured: 4 chunks)
+        const int ch_min = (c->nranks > 1 && np >= 64) ? 4 : 1;
+        for (int ch = ch_min; ch <= 16 && ch * 8 <= np; ++ch) {
             if (ch < 16 && (np + ch - 1) / ch > 256) continue;    // x-spacing table lives in shared memory
             const long long blocks = tiles * ch, waves = (blocks + slots - 1) / slots;
             const double eff = (double)blocks / (double)(waves * slots) * (1.0 - 1.5 * ch / (double)np);
@@ -569,9 +572,10 @@ struct Engine : IEngine {
                                                                    c->w, c->tt - c->w_base);
             c->launches++;
         }
-        if (c->comm && c->nranks > 1) {
+        static const int fake_edges = getenv("PHB_DEBUG_FAKE_EDGES") ? atoi(getenv("PHB_DEBUG_FAKE_EDGES")) : 0;   // timing aid
+        if ((c->comm && c->nranks > 1) || fake_edges) {
             // edge planes first so that the exchange overlaps the interior update
-            const bool hasL = c->rank > 0, hasR = c->rank < c->nranks - 1;
+            const bool hasL = c->rank > 0 || (fake_edges & 1), hasR = c->rank < c->nranks - 1 || (fake_edges & 2);
             int ib = x0, ie = xe;
             if (hasL && hasR && use_march()) {
                 OK(physics(x0, x0 + 1, xe - 1));      // both edge planes in one launch
@@ -584,7 +588,7 @@ struct Engine : IEngine {
             }
             CU(cudaEventRecord(c->ev_edge, c->st));
             CU(cudaStreamWaitEvent(c->cst, c->ev_edge, 0));
-            OK(exchange());
+            if (c->comm) OK(exchange());
             CU(cudaEventRecord(c->ev_comm, c->cst));
             OK(physics(ib, ie));
             if (last) OK(abc_x());
@@ -671,7 +675,11 @@ int phb_create(const phb_cfg *cfg, phb_ctx **out) {
     c->ps = (long long)cfg->ny * c->nzp;
     auto cleanup = [&](int r) { phb_destroy(c); return r; };
     if (cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess) return cleanup(fail("stream create failed"));
-    if (cudaStreamCreateWithFlags(&c->cst, cudaStreamNonBlocking) != cudaSuccess) return cleanup(fail("stream create failed"));
+    {   // the halo exchange must get SMs ahead of the interior stencil blocks that become runnable at the same moment
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (cudaStreamCreateWithPriority(&c->cst, cudaStreamNonBlocking, hi) != cudaSuccess) return cleanup(fail("stream create failed"));
+    }
     cudaEventCreateWithFlags(&c->ev_edge, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->ev_comm, cudaEventDisableTiming);
     cudaEventCreate(&c->ev_t0);
