@@ -1,0 +1,93 @@
+"""Parity at BASELINE sizes.
+
+* 256^3 (config #2, homogeneous) and a 256x192x160 crystal: the CUDA path against the C oracle
+  (oracle/fdtd_c.c, pinned bit-for-bit to the reference) for a few steps -- bitwise in EXACT mode,
+  <= 1e-12 in FAST mode, <= 1e-5 in fp32.
+* 512^3 crystal (config #3), where no CPU oracle is affordable: size-independent properties of
+  the scheme -- linearity in the source, y-mirror symmetry of a y-symmetric problem, causality
+  (nothing moves ahead of the numerical front), FAST vs EXACT agreement, march vs naive kernel."""
+import numpy as np
+import pytest
+
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def _c_oracle(case, ids, steps):
+    from oracle import fdtd_c
+    o = fdtd_c.COracle(case.x, case.y, case.z, ids, [case.prim_c, case.sec_c], [case.prim_p, case.sec_p], case.dt,
+                       wave=case.wave, wave_args=case.wave_args, omp=True)
+    o.run(steps)
+    out = [o.ux.copy(), o.uy.copy(), o.uz.copy()]
+    o.close()
+    return out
+
+
+@pytest.mark.parametrize("shape,homog,steps", [((256, 256, 256), True, 6), ((256, 192, 160), False, 8)])
+def test_vs_c_oracle_at_256(shape, homog, steps):
+    from phonomena_b200.workloads import crystal_case
+    case = crystal_case(*shape, homogeneous=homog)
+    with case.make_engine(steps=steps, dtype="f64", arith="exact") as e:
+        ids = e.get_material_ids()
+        e.run(steps)
+        got_exact = e.get_fields()
+        assert e.info()["kernel"] == "march_tma"
+    ref = _c_oracle(case, ids, steps)
+    assert sum(float(np.abs(a).sum()) for a in ref) > 0
+    for a, b, n in zip(got_exact, ref, "xyz"):
+        assert np.array_equal(a, b), ("u" + n, float(np.abs(a - b).max()))
+    with case.make_engine(steps=steps, dtype="f64", arith="fast") as e:
+        e.run(steps)
+        assert H.rel_l2(e.get_fields(), ref) <= 1e-12
+    with case.make_engine(steps=steps, dtype="f32", arith="fast") as e:
+        e.run(steps)
+        assert H.rel_l2(e.get_fields(), ref) <= 1e-5
+
+
+def _run512(steps, w, dtype="f64", arith="fast", kernel="auto", homog=False):
+    from phonomena_b200.workloads import crystal_case
+    case = crystal_case(512, 512, 512, homogeneous=homog)
+    e = case.make_engine(steps=steps, dtype=dtype, arith=arith, kernel=kernel)
+    e.set_source_table(np.asarray(w, np.float64))
+    e.run(steps)
+    out = e.get_fields()
+    e.close()
+    return out
+
+
+def test_512_linearity_and_causality():
+    steps = 24
+    rng = np.random.default_rng(3)
+    w1, w2 = rng.standard_normal(steps), rng.standard_normal(steps)
+    a = _run512(steps, w1)
+    b = _run512(steps, w2)
+    c = _run512(steps, 2.0 * w1 - 0.5 * w2)
+    lin = [2.0 * x - 0.5 * y for x, y in zip(a, b)]
+    assert H.rel_l2(c, lin) <= 1e-12
+    # the stencil moves information by at most one cell per step in x: beyond the front, exactly zero
+    for f in a:
+        assert np.any(f[: steps // 2] != 0)
+        assert not np.any(f[steps + 2:])
+
+
+def test_512_fast_exact_naive_agree():
+    steps = 12
+    w = np.sin(0.3 * np.arange(steps))
+    exact = _run512(steps, w, arith="exact")
+    fast = _run512(steps, w, arith="fast")
+    naive = _run512(steps, w, arith="exact", kernel="naive")
+    assert all(np.array_equal(x, y) for x, y in zip(exact, naive))      # two kernels, one arithmetic: bitwise
+    assert H.rel_l2(fast, exact) <= 1e-12
+    f32 = _run512(steps, w, dtype="f32")
+    assert H.rel_l2(f32, exact) <= 1e-5
+
+
+def test_512_y_mirror_symmetry():
+    """Homogeneous medium, uniform mesh: the problem is symmetric under y -> -y (uy odd, ux/uz even);
+    differences and sums of mirrored values round identically, so EXACT mode is symmetric bit for bit."""
+    steps = 16
+    ux, uy, uz = _run512(steps, np.sin(0.2 * np.arange(steps)), arith="exact", homog=True)
+    assert np.array_equal(ux, ux[:, ::-1, :]) and np.array_equal(uz, uz[:, ::-1, :])
+    assert np.array_equal(uy, -uy[:, ::-1, :])
+    assert np.any(uy != 0)
