@@ -251,19 +251,28 @@ def run_e2e(case, n, rank, local, K, dtype, arith, dist):
                   "slabs_from_env": n > 1, "chunk_steps": 10})
     s.file = os.path.join(tempfile.gettempdir(), "phb_bench_rank%d.h5" % rank)
     steps = max(K, 10)
-    if n > 1:
-        return None   # the plugin's multi-rank path shares the engine-level exchange measured in `value`
     s.init(g, m, steps)
+    if dist is not None:
+        import torch
+        dist.barrier()
+        torch.cuda.synchronize()
     t0 = time.perf_counter()
     s.run()
     dt = time.perf_counter() - t0
+    if dist is not None:
+        import torch
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t[0])
     nx, ny, nz = case.shape
+    path = s.file if n == 1 else "%s.rank%d" % (s.file, rank)
     out = {"value": nx * ny * nz * steps / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": 8,
            "d2h_bytes_per_step": 8 * ((nx - 1) * ny + nx * (ny - 1) + nx * ny), "steps": steps,
-           "what": "Solver.run(): source sample H2D + surface ux,uy,uz planes D2H (pinned ring) -> HDF5 every step",
-           "file_bytes": os.path.getsize(s.file)}
+           "what": "Solver.run(): source sample H2D + surface ux,uy,uz planes D2H (pinned ring) -> HDF5 every step"
+                   + ("; one slab file per rank, max over ranks" if n > 1 else ""),
+           "file_bytes": os.path.getsize(path)}
     try:
-        os.remove(s.file)
+        os.remove(path)
     except OSError:
         pass
     s._close_engine()

@@ -979,6 +979,25 @@ int phb_comm_init(phb_ctx *c, const char id[128], int32_t rank, int32_t nranks) 
     ncclUniqueId u;
     memcpy(&u, id, 128);
     NC(g_nccl.CommInitRank(&c->comm, nranks, u, rank));
+    // NCCL sets its peer connections up lazily on first use: do one tiny exchange with both neighbours now so
+    // that the first time step does not pay for it (Solver.init absorbs it, Solver.run does not)
+    {
+        double *tmp = nullptr;
+        CU(cudaMalloc(&tmp, 4 * sizeof(double)));
+        NC(g_nccl.GroupStart());
+        if (rank > 0) {
+            NC(g_nccl.Send(tmp + 0, 1, ncclDouble, rank - 1, c->comm, c->cst));
+            NC(g_nccl.Recv(tmp + 1, 1, ncclDouble, rank - 1, c->comm, c->cst));
+        }
+        if (rank < nranks - 1) {
+            NC(g_nccl.Send(tmp + 2, 1, ncclDouble, rank + 1, c->comm, c->cst));
+            NC(g_nccl.Recv(tmp + 3, 1, ncclDouble, rank + 1, c->comm, c->cst));
+        }
+        NC(g_nccl.GroupEnd());
+        cudaError_t e = cudaStreamSynchronize(c->cst);
+        cudaFree(tmp);
+        CU(e);
+    }
     return 0;
 }
 

@@ -79,12 +79,13 @@ class Writer:
         self.h5.create_dataset("density", meta["density"])
         if meta.get("elasticity") is not None:
             self.h5.create_dataset("elasticity", meta["elasticity"])
-        nx, ny, nz = engine.nx, engine.ny, engine.nz
+        ny, nz = engine.ny, engine.nz
         zext = 1 if mode == "surface" else None
+        # x extents are the planes this context owns (the whole grid, or one slab: attrs x0 / nxl)
         self.ds = {
-            "ux": self.h5.create_chunked("ux", (nx - 1, ny, zext or nz, frames)),
-            "uy": self.h5.create_chunked("uy", (nx, ny - 1, zext or nz, frames)),
-            "uz": self.h5.create_chunked("uz", (nx, ny, zext or (nz - 1), frames)),
+            "ux": self.h5.create_chunked("ux", (engine.planes(0), ny, zext or nz, frames)),
+            "uy": self.h5.create_chunked("uy", (engine.planes(1), ny - 1, zext or nz, frames)),
+            "uz": self.h5.create_chunked("uz", (engine.planes(2), ny, zext or (nz - 1), frames)),
         }
         self.written = 0
         self.error = None
@@ -189,11 +190,17 @@ class Solver:
                         device=int(c["device"]), x0=x0, nxl=nxl, kernel=c.get("kernel", "auto"),
                         record_mask=rec_mask, record_every=int(c["record_every"]), ring_slots=32)
         self.engine = e
+        if nranks > 1:
+            # one process per GPU: rank 0 makes the NCCL id, any host channel carries it (default: torch.distributed)
+            uid = self.broadcast(_lib.comm_unique_id() if rank == 0 else None)
+            e.comm_init(uid, rank, nranks)
         e.set_spacing(fdx, fdy, fdz, sdx, sdy, sdz)
         e.set_material_table([prim["c"], sec["c"]], [prim["p"], sec["p"]])
         e.gen_material_ids(targets, mx, my, mz)
         ids = e.get_material_ids() if (rec_mode != "off" or x0 == 0) else None
         corner = int(ids[0, 0, 0]) if (ids is not None and x0 == 0) else 0
+        if nranks > 1:      # the Mur coefficients come from the corner cell (0,0,0), which rank 0 owns
+            corner = int(self.broadcast(corner if rank == 0 else None))
         cm = sec if corner else prim
         e.set_abc(hm.abc_coefficients(cm["c"], cm["p"], dt, fdx, fdy, fdz, sdx, sdy, sdz))
         self.dt, self._x0 = dt, x0
@@ -207,11 +214,12 @@ class Solver:
                      "sdx": sdx.reshape(-1, 1, 1), "sdy": sdy.reshape(1, -1, 1), "sdz": sdz.reshape(1, 1, -1),
                      "fdx": fdx.reshape(-1, 1, 1), "fdy": fdy.reshape(1, -1, 1), "fdz": fdz.reshape(1, 1, -1),
                      "steps": int(self.t), "dt": float(dt), "prim_material": prim["name"], "sec_material": sec["name"],
-                     "solver_cfg": json.dumps(c)}
+                     "solver_cfg": json.dumps(c), "x0": int(x0), "nxl": int(nxl)}
             meta = {"attrs": attrs, "density": P, "elasticity": None}
             if rec_mode == "full" and P.size <= 1 << 22:      # the reference's `elasticity` is 288 B/cell
                 meta["elasticity"] = np.where((ids == 1)[..., None, None], sec["c"], prim["c"])
-            self.writer = Writer(self.file, e, meta, frames, rec_mode, int(c["record_every"]))
+            path = self.file if nranks == 1 else "%s.rank%d" % (self.file, rank)      # one file per slab
+            self.writer = Writer(path, e, meta, frames, rec_mode, int(c["record_every"]))
             self.writer.start()
         self._rec_mode = rec_mode
 
@@ -268,6 +276,16 @@ class Solver:
     def cancel(self):
         if self.running.is_set():
             self.running.clear()
+
+    def broadcast(self, obj):
+        """Broadcast a small Python object from rank 0 (multi-GPU runs).  Default channel:
+        torch.distributed, which the launcher (torchrun) has initialised; override to use another."""
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            raise RuntimeError("multi-GPU run: initialise torch.distributed (torchrun) or override Solver.broadcast")
+        box = [obj]
+        dist.broadcast_object_list(box, src=0)
+        return box[0]
 
     def test(self):
         """base_solver.py:286-292: 10 steps on the reference's TestDefaults grid (needs the reference
