@@ -117,6 +117,12 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *tm,
         ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
 template <class T, int V> struct alignas(sizeof(T) * V) Pack { T v[V]; };
 
 __device__ __forceinline__ Pack<float, 4> lds_vec(uint32_t a, float) {
@@ -187,9 +193,9 @@ template <class T> __device__ __forceinline__ T shfl_up1(T v) { return __shfl_up
 template <class T> __device__ __forceinline__ T shfl_dn1(T v) { return __shfl_down_sync(0xffffffffu, v, 1); }
 
 struct MarchMaps {
-    CUtensorMap u[3];   // u_cur components, box (34 V, R, 1)
-    CUtensorMap o[3];   // u_old components, box (32 V, TY, 1)
-    CUtensorMap c;      // class bytes,      box (32 V + 32, R, 1)
+    CUtensorMap u;      // u_cur, all three components (4-D: z, y, plane, component), box (34 V, R, 1, 3)
+    CUtensorMap o;      // u_old, all three components,                               box (32 V, TY, 1, 3)
+    CUtensorMap c;      // class bytes (3-D),                                         box (32 V + 32, R, 1)
 };
 
 // ---- the kernel ---------------------------------------------------------------------------------
@@ -266,16 +272,14 @@ k_step_march(const __grid_constant__ MarchMaps tm, StepArgs<typename A::T> p, Ma
         const int s = q % NST;
         const uint32_t dst = sb + s * C_::STAGE, bar = bar_full + s * 8;
         mbar_expect_tx(bar, C_::TX_U);
-#pragma unroll
-        for (int q3 = 0; q3 < 3; ++q3) tma_load_3d(dst + q3 * C_::UCOMP, &tm.u[q3], bar, k0t - V, j0 - 1, lbase + q);
+        tma_load_4d(dst, &tm.u, bar, k0t - V, j0 - 1, lbase + q, 0);
         tma_load_3d(dst + C_::OFF_C, &tm.c, bar, k0t - 16, j0 - 1, lbase + q);
     };
     auto issue_o = [&](int q) {
         const int s = q % NSO;
         const uint32_t dst = sb + C_::OFF_O + s * C_::OSTAGE, bar = bar_fullO + s * 8;
         mbar_expect_tx(bar, C_::TX_O);
-#pragma unroll
-        for (int q3 = 0; q3 < 3; ++q3) tma_load_3d(dst + q3 * C_::OCOMP, &tm.o[q3], bar, k0t, j0, lbase + q);
+        tma_load_4d(dst, &tm.o, bar, k0t, j0, lbase + q, 0);
     };
     // claim number c: u_cur plane c (if c < nplanes) and u_old plane c - (NST - NSO) if that plane is one
     // whose u_new is produced (1 .. nplanes-2).  Every issued load is waited for by some warp before the
@@ -559,12 +563,25 @@ inline bool make_map3(CUtensorMap *tm, CUtensorMapDataType dt, int esz, void *ba
     return enc(tm, dt, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
+// 4-D tensor map over the three components of one displacement buffer (allocated back to back):
+// dims (nzp, ny, planes, 3), box (bx, by, 1, 3).
+inline bool make_map4(CUtensorMap *tm, CUtensorMapDataType dt, int esz, void *base, int nzp, int ny, int planes, int bx,
+                      int by) {
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) return false;
+    const cuuint64_t dims[4] = {(cuuint64_t)nzp, (cuuint64_t)ny, (cuuint64_t)planes, 3};
+    const cuuint64_t strides[3] = {(cuuint64_t)nzp * esz, (cuuint64_t)nzp * ny * esz, (cuuint64_t)nzp * ny * esz * planes};
+    const cuuint32_t box[4] = {(cuuint32_t)bx, (cuuint32_t)by, 1u, 3u};
+    const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+    return enc(tm, dt, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 template <class T>
 inline bool make_field_maps(CUtensorMap *cur_box, CUtensorMap *old_box, void *base, int nzp, int ny, int planes, int R) {
     constexpr int V = VecOf<T>::V;
     const CUtensorMapDataType dt = sizeof(T) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
-    return make_map3(cur_box, dt, sizeof(T), base, nzp, ny, planes, 34 * V, R) &&
-           make_map3(old_box, dt, sizeof(T), base, nzp, ny, planes, 32 * V, R - 2);
+    return make_map4(cur_box, dt, sizeof(T), base, nzp, ny, planes, 34 * V, R) &&
+           make_map4(old_box, dt, sizeof(T), base, nzp, ny, planes, 32 * V, R - 2);
 }
 template <class T>
 inline bool make_class_map(CUtensorMap *tm, void *base, int nzp, int ny, int planes, int R) {

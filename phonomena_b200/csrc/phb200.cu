@@ -483,18 +483,18 @@ struct Engine : IEngine {
         c->maps_ok = false;
         if (c->cfg.kernel == PHB_KERNEL_NAIVE || !c->code) return 0;
         const int planes = c->cfg.nxl + 2;
-        CUtensorMap cur[3][3], old[3][3], cls;
+        CUtensorMap cur[3], old[3], cls;
         bool ok = make_class_map<T>(&cls, c->code, c->nzp, c->cfg.ny, planes, c->mR);
-        for (int b = 0; b < 3 && ok; ++b)
-            for (int q = 0; q < 3 && ok; ++q)
-                ok = make_field_maps<T>(&cur[b][q], &old[b][q], c->buf[b][q], c->nzp, c->cfg.ny, planes, c->mR);
+        for (int b = 0; b < 3 && ok; ++b)      // the three components of a buffer are one allocation
+            ok = make_field_maps<T>(&cur[b], &old[b], c->buf[b][0], c->nzp, c->cfg.ny, planes, c->mR);
         if (!ok) {
             if (c->cfg.kernel == PHB_KERNEL_MARCH) return fail("cuTensorMapEncodeTiled failed");
             return 0;
         }
         for (int b = 0; b < 3; ++b) {
             const int bo = (b + 2) % 3;
-            for (int q = 0; q < 3; ++q) { c->mm[b].u[q] = cur[b][q]; c->mm[b].o[q] = old[bo][q]; }
+            c->mm[b].u = cur[b];
+            c->mm[b].o = old[bo];
             c->mm[b].c = cls;
         }
         c->maps_ok = true;
@@ -685,9 +685,11 @@ int phb_create(const phb_cfg *cfg, phb_ctx **out) {
     cudaEventCreate(&c->ev_t0);
     cudaEventCreate(&c->ev_t1);
     const size_t fb = (size_t)(cfg->nxl + 2) * c->ps * c->esz;
-    for (int b = 0; b < 3; ++b)
-        for (int q = 0; q < 3; ++q)
-            if (dmalloc(c, &c->buf[b][q], fb)) return cleanup(1);
+    for (int b = 0; b < 3; ++b) {          // ux, uy, uz of a buffer back to back (one 4-D TMA descriptor covers them)
+        if (dmalloc(c, &c->buf[b][0], 3 * fb)) return cleanup(1);
+        c->buf[b][1] = (char *)c->buf[b][0] + fb;
+        c->buf[b][2] = (char *)c->buf[b][0] + 2 * fb;
+    }
     if (dmalloc(c, &c->line_save, (size_t)cfg->ny * c->esz)) return cleanup(1);
     if (cfg->dtype == PHB_F64) c->eng = new Engine<double>(c); else c->eng = new Engine<float>(c);
     if (const char *e = getenv("PHB_MARCH_R")) c->mR = atoi(e);
@@ -724,8 +726,7 @@ int phb_destroy(phb_ctx *c) {
     if (c->st) cudaStreamSynchronize(c->st);
     if (c->cst) cudaStreamSynchronize(c->cst);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
-    for (int b = 0; b < 3; ++b)
-        for (int q = 0; q < 3; ++q) cudaFree(c->buf[b][q]);
+    for (int b = 0; b < 3; ++b) cudaFree(c->buf[b][0]);
     for (int a = 0; a < 6; ++a) cudaFree(c->sp[a]);
     cudaFree(c->tab); cudaFree(c->ids); cudaFree(c->code); cudaFree(c->line_save);
     if (c->w) cudaFree(c->w);
