@@ -163,11 +163,18 @@ def run_b200(args):
     K, W = args.steps, args.warmup
     dtype, arith = args.dtype, args.arith
     e = case.make_engine(steps=W + K, x0=x0, nxl=nxl, dtype=dtype, arith=arith, device=local, kernel=args.kernel)
+    halo = "none"
     if world > 1:
-        import torch
-        uid = [_lib.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        e.comm_init(uid[0], rank, world)
+        def allgather(obj):
+            out = [None] * world
+            dist.all_gather_object(out, obj)
+            return out
+
+        def broadcast(obj):
+            box = [obj]
+            dist.broadcast_object_list(box, src=0)
+            return box[0]
+        halo = e.connect(rank, world, allgather, broadcast)
 
     def barrier():
         if dist is not None:
@@ -228,7 +235,9 @@ def run_b200(args):
                                "Mur ABC + free surface + left-wall sin source f=100, courant 0.1" % (nx, NY, NZ, "3" if n == 1 else "5", NX_PER_GPU),
                    "arith": arith, "material": "indexed (1-byte stencil class)", "kernel": info["kernel"],
                    "l2": "inputs (%.1f GB/GPU) far exceed the 126 MB L2; no explicit flush" % (info["device_bytes"] / 1e9),
-                   "halo": "NCCL send/recv of 3 planes per direction per step, overlapped with the interior update" if n > 1 else "none"},
+                   "halo": {"none": "none", "nccl": "NCCL send/recv of 3 planes per direction per step, overlapped with the interior update",
+                            "p2p": "fused: the stencil kernel stores its edge planes into the neighbours' ghost planes over NVLink (CUDA IPC), "
+                                   "stream-ordered flag write/wait, no collective call"}[halo]},
         "clocks": clocks, "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None,
                      "traffic": traffic, "peak_source": peak_src, "kernel": "k_step_march", "kernel_ms_per_step": kms / K if K else None, "kernel_launches_per_step": kn / K if K else None,

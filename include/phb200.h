@@ -138,6 +138,16 @@ int phb_profile(phb_ctx *ctx, int32_t enable, double *kernel_ms, int64_t *kernel
 int phb_comm_unique_id(char id[128]);
 int phb_comm_init(phb_ctx *ctx, const char id[128], int32_t rank, int32_t nranks);
 
+/* Fused halo exchange over NVLink peer memory (preferred over the NCCL path): every rank exports CUDA-IPC
+ * handles of its three displacement buffers and of its flag word (4 x 64 bytes) plus its nxl; the host
+ * hands each rank the exports of its left and right neighbours (NULL at the ends).  The stencil kernel then
+ * stores the slab's first / last plane straight into the neighbours' ghost planes; a stream-ordered flag
+ * write / wait replaces the collective; each rank applies the y / z absorbing faces to its ghost planes.
+ * replaces: nothing in the reference. */
+int phb_p2p_export(phb_ctx *ctx, char handles[256], int32_t *nxl);
+int phb_p2p_import(phb_ctx *ctx, int32_t rank, int32_t nranks, const char *left, int32_t left_nxl,
+                   const char *right, int32_t right_nxl);
+
 /* surface recording: replaces Grid.freezeData + Writer.put (grid.py:68-77,
  * base_solver.py:97-100,258-260) for the k=0 plane.  Frames are written by the device
  * into a pinned host ring; the consumer takes them in order.

@@ -25,7 +25,7 @@ SYMBOLS = (
     "phb_set_spacing", "phb_set_material_table", "phb_set_material_ids", "phb_gen_material_ids",
     "phb_get_material_ids", "phb_set_abc", "phb_set_source_table", "phb_set_fields", "phb_get_fields",
     "phb_get_stress", "phb_run", "phb_sync", "phb_run_timed", "phb_steps_done", "phb_launch_count",
-    "phb_info", "phb_profile", "phb_comm_unique_id", "phb_comm_init", "phb_record_next", "phb_record_release",
+    "phb_info", "phb_profile", "phb_comm_unique_id", "phb_comm_init", "phb_p2p_export", "phb_p2p_import", "phb_record_next", "phb_record_release",
     "phb_record_frame_doubles",
 )
 
@@ -84,6 +84,8 @@ def load_library(path=None):
     lib.phb_profile.argtypes = [vp, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     lib.phb_comm_unique_id.argtypes = [C.c_char_p]
     lib.phb_comm_init.argtypes = [vp, C.c_char_p, C.c_int32, C.c_int32]
+    lib.phb_p2p_export.argtypes = [vp, C.c_char_p, C.POINTER(C.c_int32)]
+    lib.phb_p2p_import.argtypes = [vp, C.c_int32, C.c_int32, C.c_char_p, C.c_int32, C.c_char_p, C.c_int32]
     lib.phb_record_next.argtypes = [vp, C.POINTER(dp), C.POINTER(C.c_int64), C.c_int32]
     lib.phb_record_release.argtypes = [vp]
     lib.phb_record_frame_doubles.argtypes = [vp, C.POINTER(C.c_int64)]
@@ -282,6 +284,37 @@ class Engine:
     # -- multi-GPU ----------------------------------------------------------------------
     def comm_init(self, unique_id, rank, nranks):
         _chk(self.lib, self.lib.phb_comm_init(self._ctx, unique_id, int(rank), int(nranks)))
+
+    def p2p_export(self):
+        """(256-byte IPC handle blob, nxl) for the fused NVLink halo push."""
+        buf, nxl = C.create_string_buffer(256), C.c_int32(0)
+        _chk(self.lib, self.lib.phb_p2p_export(self._ctx, buf, C.byref(nxl)))
+        return buf.raw, nxl.value
+
+    def p2p_import(self, rank, nranks, exports):
+        """exports: list over ranks of p2p_export() results."""
+        left = exports[rank - 1] if rank > 0 else (None, 0)
+        right = exports[rank + 1] if rank < nranks - 1 else (None, 0)
+        _chk(self.lib, self.lib.phb_p2p_import(self._ctx, int(rank), int(nranks), left[0], int(left[1]), right[0], int(right[1])))
+
+    def connect(self, rank, nranks, allgather, broadcast, mode=None):
+        """Set up the halo exchange of an x-slab context.  mode 'p2p' (default: fused NVLink peer stores,
+        CUDA IPC) or 'nccl'; `allgather(obj) -> list` and `broadcast(obj) -> obj` are host channels."""
+        import os
+        mode = mode or os.environ.get("PHB_HALO", "p2p")
+        if nranks == 1:
+            return "none"
+        if mode == "p2p":
+            ok = 1
+            try:
+                exports = allgather(self.p2p_export())
+                self.p2p_import(rank, nranks, exports)
+            except PhbError:
+                ok = 0
+            if all(allgather(ok)):
+                return "p2p"
+        self.comm_init(broadcast(comm_unique_id() if rank == 0 else None), rank, nranks)
+        return "nccl"
 
     # -- recorder -----------------------------------------------------------------------
     def frame_doubles(self):

@@ -107,6 +107,17 @@ __global__ void k_abc_z(AbcArgs<typename A::T> p) {
 }
 
 // ---------------------------------------------------------------------------------------
+// Fused halo push: after the stencil kernel has stored the edge planes into the neighbours' ghost
+// planes, tell them which step is complete (flags live in the NEIGHBOUR's memory, CUDA IPC).
+// ---------------------------------------------------------------------------------------
+__global__ void k_signal(volatile int *left_flag, volatile int *right_flag, int step) {
+    __threadfence_system();
+    if (left_flag) *left_flag = step;
+    if (right_flag) *right_flag = step;
+    __threadfence_system();
+}
+
+// ---------------------------------------------------------------------------------------
 // Layout conversion between host arrays (float64, reference shapes, plane-major) and the
 // padded device box.  src/dst host-shaped array: (np, ey, ez); device plane l0 + p.
 // ---------------------------------------------------------------------------------------

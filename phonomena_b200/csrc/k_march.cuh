@@ -199,7 +199,7 @@ struct MarchMaps {
 };
 
 // ---- the kernel ---------------------------------------------------------------------------------
-template <class A, int R, int NST>
+template <class A, int R, int NST, bool PUSH>
 __global__ void __launch_bounds__(R * 32, (R <= 8 ? 2 : 1))
 k_step_march(const __grid_constant__ MarchMaps tm, StepArgs<typename A::T> p, MatCls<typename A::T> m, int chunk) {
     using T = typename A::T;
@@ -508,6 +508,23 @@ k_step_march(const __grid_constant__ MarchMaps tm, StepArgs<typename A::T> p, Ma
                 *reinterpret_cast<PV *>(p.nw.ux + off) = ox;
                 *reinterpret_cast<PV *>(p.nw.uy + off) = oy;
                 *reinterpret_cast<PV *>(p.nw.uz + off) = oz;
+                // fused halo exchange: the slab's edge planes go straight into the neighbours' ghost planes over NVLink
+                if constexpr (PUSH) {
+                if (n == g.x0 && p.push_lo[0]) {
+                    const int po = j * g.nzp + kb;
+                    *reinterpret_cast<PV *>(p.push_lo[0] + po) = ox;
+                    *reinterpret_cast<PV *>(p.push_lo[1] + po) = oy;
+                    *reinterpret_cast<PV *>(p.push_lo[2] + po) = oz;
+                    __threadfence_system();       // out before the stream-ordered flag write that follows the kernel
+                }
+                if (n == g.x0 + g.nxl - 1 && p.push_hi[0]) {
+                    const int po = j * g.nzp + kb;
+                    *reinterpret_cast<PV *>(p.push_hi[0] + po) = ox;
+                    *reinterpret_cast<PV *>(p.push_hi[1] + po) = oy;
+                    *reinterpret_cast<PV *>(p.push_hi[2] + po) = oz;
+                    __threadfence_system();
+                }
+                }
             }
         }
         // every read this warp makes of the stage holding plane n is done
@@ -591,12 +608,15 @@ inline bool make_class_map(CUtensorMap *tm, void *base, int nzp, int ny, int pla
 template <class T> inline const char *march_name() { return "march_tma"; }
 
 // returns launches made (1), 0 for an empty range, -1 if the shared-memory request is refused
-template <class A, int R, int NST>
+template <class A, int R, int NST, bool PUSH = false>
 inline int launch_march_cfg(const StepArgs<typename A::T> &p, const MatCls<typename A::T> &m, const MarchMaps &maps,
                             int chunks, cudaStream_t st) {
     using T = typename A::T;
     using C_ = MarchCfg<T, R, NST>;
-    auto kern = k_step_march<A, R, NST>;
+    if constexpr (!PUSH) {
+        if (p.push_lo[0] || p.push_hi[0]) return launch_march_cfg<A, R, NST, true>(p, m, maps, chunks, st);
+    }
+    auto kern = k_step_march<A, R, NST, PUSH>;
     static size_t attr_bytes = 0;   // per template instantiation
     const int np = p.i_end - p.i_begin;
     if (np <= 0) return 0;

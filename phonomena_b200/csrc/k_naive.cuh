@@ -13,6 +13,9 @@ struct StepArgs {
     Fld<T> cur, old, nw;
     const T *line_save;   // pre-source uz(0, j, 0) of `cur` (App. B #9), or nullptr
     int i_begin, i_end;   // global planes to update: [i_begin, i_end)
+    // fused halo push (k_march only): where the first / last owned plane of u_new also goes -- the matching ghost
+    // plane of the left / right neighbour's buffer, mapped through CUDA IPC (NVLink peer stores); null = none
+    T *push_lo[3], *push_hi[3];
     int edge_b;           // >= 0: second single plane of an 'edge launch' (planes i_begin and edge_b, one chunk each)
 };
 

@@ -2,6 +2,7 @@
 // orchestration, NCCL halo exchange, pinned-ring surface recorder.  sm_100a only.
 #include "../../include/phb200.h"
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <nccl.h>
@@ -139,6 +140,12 @@ struct phb_ctx {
     // comm
     ncclComm_t comm = nullptr;
     int rank = 0, nranks = 1;
+    // fused halo push over NVLink peer memory (CUDA IPC); halo = 0 none, 1 NCCL, 2 peer stores
+    int halo = 0;
+    void *peer_buf[2][3] = {};   // [left | right][buffer]: the neighbour's displacement buffers, mapped
+    int peer_nxl[2] = {0, 0};
+    int *flags = nullptr;        // [0] written by the left neighbour, [1] by the right one: last step pushed
+    int *peer_flags[2] = {};     // the neighbours' flag arrays, mapped
     // recorder
     double *ring = nullptr;    // pinned host, mapped
     double *ring_dev = nullptr;   // device staging ring (same slots): the gather kernel runs at HBM speed,
@@ -408,6 +415,18 @@ struct Engine : IEngine {
         if (ie <= ib) return 0;
         StepArgs<T> p;
         p.edge_b = edge_b;
+        for (int q = 0; q < 3; ++q) p.push_lo[q] = p.push_hi[q] = nullptr;
+        if (c->halo == 2 && use_march()) {
+            const int bn = b_new();
+            if (c->peer_buf[0][bn]) {       // left neighbour: its right ghost plane (local plane nxl_L + 1)
+                const long long comp = (long long)(c->peer_nxl[0] + 2) * c->ps;
+                for (int q = 0; q < 3; ++q) p.push_lo[q] = (T *)c->peer_buf[0][bn] + q * comp + (long long)(c->peer_nxl[0] + 1) * c->ps;
+            }
+            if (c->peer_buf[1][bn]) {       // right neighbour: its left ghost plane (local plane 0)
+                const long long comp = (long long)(c->peer_nxl[1] + 2) * c->ps;
+                for (int q = 0; q < 3; ++q) p.push_hi[q] = (T *)c->peer_buf[1][bn] + q * comp;
+            }
+        }
         p.g = geo();
         p.cur = fld(b_cur()); p.old = fld(b_old()); p.nw = fld(b_new());
         p.line_save = (c->w && c->cfg.x0 == 0) ? (const T *)c->line_save : nullptr;
@@ -438,7 +457,6 @@ struct Engine : IEngine {
                 if (c->mR == 16 && c->mNST == 4) r = launch_march_cfg<A, 16, 4>(p, m, mp, ch, c->st);
                 else if (c->mR == 16 && c->mNST == 3) r = launch_march_cfg<A, 16, 3>(p, m, mp, ch, c->st);
                 else if (c->mR == 8 && c->mNST == 4) r = launch_march_cfg<A, 8, 4>(p, m, mp, ch, c->st);
-                else if (c->mR == 8 && c->mNST == 3) r = launch_march_cfg<A, 8, 3>(p, m, mp, ch, c->st);
                 if (r == -2) return fail("no marching-kernel instantiation for R=%d NST=%d", c->mR, c->mNST);
                 if (r < 0) return fail("marching kernel needs more shared memory than the device allows (%d classes)", c->ncls);
                 c->launches += r;
@@ -539,6 +557,21 @@ struct Engine : IEngine {
         return 0;
     }
 
+    int wait_flag(int *flag, int value) {
+        typedef CUresult (*PFN_wait)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+        static PFN_wait fn = nullptr;
+        if (!fn) {
+            void *q = nullptr;
+            cudaDriverEntryPointQueryResult qres;
+            if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &q, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess)
+                return fail("cuStreamWaitValue32 not available");
+            fn = (PFN_wait)q;
+        }
+        if (fn((CUstream)c->st, (CUdeviceptr)flag, (cuuint32_t)value, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
+            return fail("cuStreamWaitValue32 failed");
+        return 0;
+    }
+
     int exchange() {
         // send new[x0] to the left neighbour (its right ghost), new[x0+nxl-1] to the right
         // neighbour (its left ghost); receive the mirror images.  3 components per direction.
@@ -571,6 +604,25 @@ struct Engine : IEngine {
             k_source<T><<<(c->cfg.ny + 127) / 128, 128, 0, c->st>>>(geo(), (T *)c->buf[b_cur()][2], (T *)c->line_save,
                                                                    c->w, c->tt - c->w_base);
             c->launches++;
+        }
+        if (c->halo == 2 && c->nranks > 1) {
+            // ONE stencil launch: the edge planes are pushed into the neighbours' ghost planes by the kernel itself;
+            // then a stream-ordered flag write / wait (no NCCL kernel, no SM taken from the stencil), and the y / z
+            // absorbing faces are applied to the owned planes AND to the received ghost planes (same formula and
+            // inputs as on the owning rank, so the result stays bit-identical).
+            if (!use_march()) return fail("halo=p2p needs the marching kernel");
+            const bool hasL = c->rank > 0, hasR = c->rank < c->nranks - 1;
+            OK(physics(x0, xe));
+            const int stepno = (int)(c->tt + 1);
+            k_signal<<<1, 1, 0, c->st>>>(hasL ? c->peer_flags[0] + 1 : nullptr, hasR ? c->peer_flags[1] + 0 : nullptr, stepno);
+            c->launches++;
+            if (hasL) OK(wait_flag(c->flags + 0, stepno));
+            if (hasR) OK(wait_flag(c->flags + 1, stepno));
+            if (last) OK(abc_x());
+            OK(abc_yz(x0 - (hasL ? 1 : 0), xe + (hasR ? 1 : 0)));
+            c->cur = b_new();
+            c->tt++;
+            return 0;
         }
         static const int fake_edges = getenv("PHB_DEBUG_FAKE_EDGES") ? atoi(getenv("PHB_DEBUG_FAKE_EDGES")) : 0;   // timing aid
         if ((c->comm && c->nranks > 1) || fake_edges) {
@@ -726,6 +778,11 @@ int phb_destroy(phb_ctx *c) {
     if (c->st) cudaStreamSynchronize(c->st);
     if (c->cst) cudaStreamSynchronize(c->cst);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    for (int s = 0; s < 2; ++s) {
+        for (int b = 0; b < 3; ++b) if (c->peer_buf[s][b]) cudaIpcCloseMemHandle(c->peer_buf[s][b]);
+        if (c->peer_flags[s]) cudaIpcCloseMemHandle(c->peer_flags[s]);
+    }
+    cudaFree(c->flags);
     for (int b = 0; b < 3; ++b) cudaFree(c->buf[b][0]);
     for (int a = 0; a < 6; ++a) cudaFree(c->sp[a]);
     cudaFree(c->tab); cudaFree(c->ids); cudaFree(c->code); cudaFree(c->line_save);
@@ -901,7 +958,7 @@ static int run_locked(phb_ctx *c, int64_t nsteps) {
     if (!c->have_spacing) return fail("phb_set_spacing not called");
     if (!c->code) return fail("material not set (table + ids)");
     if (!c->have_abc) return fail("phb_set_abc not called");
-    if (c->nranks > 1 && !c->comm) return fail("slab context without communicator: call phb_comm_init");
+    if (c->nranks > 1 && !c->comm && c->halo != 2) return fail("slab context without halo exchange: call phb_comm_init or phb_p2p_import");
     for (int64_t s = 0; s < nsteps; ++s) {
         OK(c->eng->step());
         if (c->cfg.record_mask && (c->tt % c->cfg.record_every) == 0) OK(record_frame(c));
@@ -976,6 +1033,7 @@ int phb_comm_init(phb_ctx *c, const char id[128], int32_t rank, int32_t nranks) 
     c->rank = rank; c->nranks = nranks;
     if (nranks == 1) return 0;
     if (c->cfg.nxl < 4) return fail("a slab needs at least 4 planes (got %d)", c->cfg.nxl);
+    c->halo = 1;
     OK(nccl_load());
     ncclUniqueId u;
     memcpy(&u, id, 128);
@@ -999,6 +1057,44 @@ int phb_comm_init(phb_ctx *c, const char id[128], int32_t rank, int32_t nranks) 
         cudaFree(tmp);
         CU(e);
     }
+    return 0;
+}
+
+int phb_p2p_export(phb_ctx *c, char handles[256], int32_t *nxl) {
+    ENTER(c);
+    if (!c->flags) {
+        OK(dmalloc(c, (void **)&c->flags, 64));
+        CU(cudaStreamSynchronize(c->st));
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+    for (int b = 0; b < 3; ++b) CU(cudaIpcGetMemHandle((cudaIpcMemHandle_t *)(handles + 64 * b), c->buf[b][0]));
+    CU(cudaIpcGetMemHandle((cudaIpcMemHandle_t *)(handles + 192), c->flags));
+    *nxl = c->cfg.nxl;
+    return 0;
+}
+
+int phb_p2p_import(phb_ctx *c, int32_t rank, int32_t nranks, const char *left, int32_t left_nxl, const char *right,
+                   int32_t right_nxl) {
+    ENTER(c);
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail("bad rank %d of %d", rank, nranks);
+    if (!c->flags) return fail("call phb_p2p_export first");
+    c->rank = rank; c->nranks = nranks;
+    if (nranks == 1) return 0;
+    if (c->cfg.nxl < 4) return fail("a slab needs at least 4 planes (got %d)", c->cfg.nxl);
+    const char *src[2] = {rank > 0 ? left : nullptr, rank < nranks - 1 ? right : nullptr};
+    const int nx2[2] = {left_nxl, right_nxl};
+    for (int s = 0; s < 2; ++s) {
+        if (!src[s]) continue;
+        cudaIpcMemHandle_t h;
+        for (int b = 0; b < 3; ++b) {
+            memcpy(&h, src[s] + 64 * b, 64);
+            CU(cudaIpcOpenMemHandle(&c->peer_buf[s][b], h, cudaIpcMemLazyEnablePeerAccess));
+        }
+        memcpy(&h, src[s] + 192, 64);
+        CU(cudaIpcOpenMemHandle((void **)&c->peer_flags[s], h, cudaIpcMemLazyEnablePeerAccess));
+        c->peer_nxl[s] = nx2[s];
+    }
+    c->halo = 2;
     return 0;
 }
 

@@ -191,9 +191,9 @@ class Solver:
                         record_mask=rec_mask, record_every=int(c["record_every"]), ring_slots=32)
         self.engine = e
         if nranks > 1:
-            # one process per GPU: rank 0 makes the NCCL id, any host channel carries it (default: torch.distributed)
-            uid = self.broadcast(_lib.comm_unique_id() if rank == 0 else None)
-            e.comm_init(uid, rank, nranks)
+            # one process per GPU: fused NVLink halo push (CUDA IPC handles all-gathered over any host channel,
+            # default torch.distributed), NCCL send/recv as fallback
+            self.halo = e.connect(rank, nranks, self.allgather, self.broadcast, mode=c.get("halo"))
         e.set_spacing(fdx, fdy, fdz, sdx, sdy, sdz)
         e.set_material_table([prim["c"], sec["c"]], [prim["p"], sec["p"]])
         e.gen_material_ids(targets, mx, my, mz)
@@ -276,6 +276,15 @@ class Solver:
     def cancel(self):
         if self.running.is_set():
             self.running.clear()
+
+    def allgather(self, obj):
+        """All-gather a small Python object over the ranks (multi-GPU runs); see broadcast()."""
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            raise RuntimeError("multi-GPU run: initialise torch.distributed (torchrun) or override Solver.allgather")
+        out = [None] * dist.get_world_size()
+        dist.all_gather_object(out, obj)
+        return out
 
     def broadcast(self, obj):
         """Broadcast a small Python object from rank 0 (multi-GPU runs).  Default channel:

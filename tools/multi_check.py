@@ -20,14 +20,23 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     nx, ny, nz = [int(v) for v in os.environ.get("PHB_MC_GRID", "96,72,80").split(",")]
     steps = int(os.environ.get("PHB_MC_STEPS", "40"))
+    def allgather(obj):
+        out = [None] * world
+        dist.all_gather_object(out, obj)
+        return out
+
+    def broadcast(obj):
+        box = [obj]
+        dist.broadcast_object_list(box, src=0)
+        return box[0]
+
+    halo = os.environ.get("PHB_HALO", "p2p")
     ok = True
     for dtype, arith, kernel in (("f64", "fast", "march"), ("f64", "exact", "march"), ("f32", "fast", "march"), ("f64", "fast", "naive")):
         case = crystal_case(nx, ny, nz)
         x0, nxl = hm.split_slabs(nx, world)[rank]
         e = case.make_engine(steps=steps, x0=x0, nxl=nxl, dtype=dtype, arith=arith, device=local, kernel=kernel)
-        uid = [_lib.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        e.comm_init(uid[0], rank, world)
+        mode = e.connect(rank, world, allgather, broadcast, mode=halo if kernel == "march" else "nccl")
         e.run(steps)
         e.sync()
         mine = e.get_fields()
@@ -42,7 +51,7 @@ def main():
         t = torch.tensor([1.0 if same else 0.0, nrm], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         if rank == 0:
-            print(json.dumps({"dtype": dtype, "arith": arith, "kernel": kernel, "ranks_identical": int(t[0]), "world": world,
+            print(json.dumps({"halo": mode, "dtype": dtype, "arith": arith, "kernel": kernel, "ranks_identical": int(t[0]), "world": world,
                               "energy": float(t[1])}), flush=True)
         ok = ok and int(t[0]) == world and float(t[1]) > 0
     dist.destroy_process_group()
