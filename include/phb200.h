@@ -39,7 +39,11 @@ enum { PHB_F32 = 0, PHB_F64 = 1 };
  *  PHB_FAST : reciprocal spacings, FMA contraction allowed (fp64: <= 1e-12 rel-L2 of the reference)
  *  PHB_EXACT: true IEEE division, the reference's expression order, no contraction:
  *             fp64 results are BIT-IDENTICAL to the reference's NumPy evaluation. */
-enum { PHB_FAST = 0, PHB_EXACT = 1 };
+enum { PHB_FAST = 0, PHB_EXACT = 1, PHB_COMP = 2 };
+/*  PHB_COMP : FAST arithmetic on the compensated state (u, delta = u - u_old) instead of (u, u_old):
+ *             delta += dt^2/rho * div T;  u_new = u + delta.  Same step algebraically; keeps fp32 within
+ *             1e-5 of the reference over >= 10^4 steps (plain fp32 drifts to 6e-5), at 12 instead of 9
+ *             field words of traffic per cell. */
 /* stencil kernel selection */
 enum { PHB_KERNEL_AUTO = 0, PHB_KERNEL_NAIVE = 1, PHB_KERNEL_MARCH = 2 };
 /* which displacement buffer */

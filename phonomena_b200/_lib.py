@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libphb200.so")
 
 F32, F64 = 0, 1
-FAST, EXACT = 0, 1
+FAST, EXACT, COMP = 0, 1, 2
 KERNEL_AUTO, KERNEL_NAIVE, KERNEL_MARCH = 0, 1, 2
 CUR, OLD = 0, 1
 REC_UX, REC_UY, REC_UZ = 1, 2, 4
@@ -138,7 +138,7 @@ class Engine:
         self.x0 = int(x0)
         self.nxl = int(self.nx - self.x0 if nxl is None else nxl)
         self.dtype = {"f32": F32, "fp32": F32, "f64": F64, "fp64": F64}[dtype]
-        self.arith = {"fast": FAST, "exact": EXACT}[arith]
+        self.arith = {"fast": FAST, "exact": EXACT, "compensated": COMP, "comp": COMP}[arith]
         cfg = Cfg()
         cfg.nx, cfg.ny, cfg.nz, cfg.x0, cfg.nxl = self.nx, self.ny, self.nz, self.x0, self.nxl
         cfg.dtype, cfg.arith, cfg.device = self.dtype, self.arith, int(device)

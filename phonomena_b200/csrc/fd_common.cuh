@@ -26,10 +26,16 @@ __device__ __forceinline__ float rn_sub(float a, float b) { return __fsub_rn(a, 
 __device__ __forceinline__ float rn_mul(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ float rn_div(float a, float b) { return __fdiv_rn(a, b); }
 
-template <class T_, bool EXACT_>
+// COMP (FAST arithmetic only): the state is (u, delta = u - u_old) instead of (u, u_old);
+//   delta_new = delta + (d2/rho) * acc,  u_new = u + delta_new
+// -- algebraically the same step, but the rounding of u no longer feeds back through the two-step
+// recurrence, which is what makes plain fp32 drift past 1e-5 after ~10^4 steps.
+template <class T_, bool EXACT_, bool COMP_ = false>
 struct Ar {
     using T = T_;
     static constexpr bool EXACT = EXACT_;
+    static constexpr bool COMP = COMP_;
+    static_assert(!(EXACT_ && COMP_), "the compensated state is a FAST-arithmetic mode");
     static __device__ __forceinline__ T add(T a, T b) {
         if constexpr (EXACT) return rn_add(a, b); else return a + b;
     }

@@ -32,10 +32,18 @@ __device__ __forceinline__ typename A::T mur(typename A::T q_inner, typename A::
     return A::add(q_inner, A::mul(c, A::sub(qn_inner, q_face)));
 }
 
+#define PHB_FACE(Q, F, N, C)                                          \
+    {                                                                 \
+        const T v_ = mur<A>(p.cur.Q[N], p.nw.Q[N], p.cur.Q[F], C);    \
+        p.nw.Q[F] = v_;                                               \
+        if constexpr (A::COMP) p.dl.Q[F] = v_ - p.cur.Q[F];           \
+    }
+
 template <class T>
 struct AbcArgs {
     Geo<T> g;
     Fld<T> cur, nw;
+    Fld<T> dl;            // COMP state: delta arrays (a face value replaces u_new, so delta = u_new - u is refreshed)
     T clx, ctx, cly0, cty0, cly1, cty1, clz, ctz;
     int i_begin, i_end;   // owned planes the y/z faces cover
 };
@@ -50,11 +58,11 @@ __global__ void k_abc_x(AbcArgs<typename A::T> p) {
     if (k >= g.nz || j >= g.ny) return;
     {   // ux: planes nx-2 (face), nx-3 (inner)
         const long long f = g.idx(g.nx - 2, j, k), n = g.idx(g.nx - 3, j, k);
-        p.nw.ux[f] = mur<A>(p.cur.ux[n], p.nw.ux[n], p.cur.ux[f], p.clx);
+        PHB_FACE(ux, f, n, p.clx)
     }
     const long long f = g.idx(g.nx - 1, j, k), n = g.idx(g.nx - 2, j, k);
-    if (j < g.ny - 1) p.nw.uy[f] = mur<A>(p.cur.uy[n], p.nw.uy[n], p.cur.uy[f], p.ctx);
-    if (k < g.nz - 1) p.nw.uz[f] = mur<A>(p.cur.uz[n], p.nw.uz[n], p.cur.uz[f], p.ctx);
+    if (j < g.ny - 1) PHB_FACE(uy, f, n, p.ctx)
+    if (k < g.nz - 1) PHB_FACE(uz, f, n, p.ctx)
 }
 
 // y = 0 (blockIdx.z == 0) and y = -1 (blockIdx.z == 1) faces.  threads over (i, k).
@@ -70,17 +78,17 @@ __global__ void k_abc_y(AbcArgs<typename A::T> p) {
     if (i < g.nx - 1) {                       // ux: rows 0|ny-1, inner 1|ny-2
         const int jf = hi ? g.ny - 1 : 0, jn = hi ? g.ny - 2 : 1;
         const long long f = g.idx(i, jf, k), n = g.idx(i, jn, k);
-        p.nw.ux[f] = mur<A>(p.cur.ux[n], p.nw.ux[n], p.cur.ux[f], ct);
+        PHB_FACE(ux, f, n, ct)
     }
     {                                         // uy: rows 0|ny-2, inner 1|ny-3
         const int jf = hi ? g.ny - 2 : 0, jn = hi ? g.ny - 3 : 1;
         const long long f = g.idx(i, jf, k), n = g.idx(i, jn, k);
-        p.nw.uy[f] = mur<A>(p.cur.uy[n], p.nw.uy[n], p.cur.uy[f], cl);
+        PHB_FACE(uy, f, n, cl)
     }
     if (k < g.nz - 1) {                       // uz: rows 0|ny-1
         const int jf = hi ? g.ny - 1 : 0, jn = hi ? g.ny - 2 : 1;
         const long long f = g.idx(i, jf, k), n = g.idx(i, jn, k);
-        p.nw.uz[f] = mur<A>(p.cur.uz[n], p.nw.uz[n], p.cur.uz[f], ct);
+        PHB_FACE(uz, f, n, ct)
     }
 }
 
@@ -94,15 +102,15 @@ __global__ void k_abc_z(AbcArgs<typename A::T> p) {
     if (j >= g.ny || i >= p.i_end) return;
     if (i < g.nx - 1) {
         const long long f = g.idx(i, j, g.nz - 1), n = f - 1;
-        p.nw.ux[f] = mur<A>(p.cur.ux[n], p.nw.ux[n], p.cur.ux[f], p.ctz);
+        PHB_FACE(ux, f, n, p.ctz)
     }
     if (j < g.ny - 1) {
         const long long f = g.idx(i, j, g.nz - 1), n = f - 1;
-        p.nw.uy[f] = mur<A>(p.cur.uy[n], p.nw.uy[n], p.cur.uy[f], p.ctz);
+        PHB_FACE(uy, f, n, p.ctz)
     }
     {
         const long long f = g.idx(i, j, g.nz - 2), n = f - 1;
-        p.nw.uz[f] = mur<A>(p.cur.uz[n], p.nw.uz[n], p.cur.uz[f], p.clz);
+        PHB_FACE(uz, f, n, p.clz)
     }
 }
 
@@ -136,6 +144,26 @@ __global__ void k_gather(const T *src, double *dst, int np, int ey, int ez, int 
     const int p = blockIdx.z;
     if (k >= ez || j >= ey || p >= np) return;
     dst[((long long)p * ey + j) * ez + k] = (double)src[((long long)(l0 + p) * ny + j) * nzp + k];
+}
+
+// COMP state: the `old` slot holds delta = u - u_old.  Host-side "u_old" <-> device delta.
+template <class T>
+__global__ void k_scatter_delta(const double *src_old, const T *cur, T *delta, int np, int ey, int ez, int l0, int ny, int nzp) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    const int p = blockIdx.z;
+    if (k >= ez || j >= ey || p >= np) return;
+    const long long d = ((long long)(l0 + p) * ny + j) * nzp + k;
+    delta[d] = (T)((double)cur[d] - src_old[((long long)p * ey + j) * ez + k]);
+}
+template <class T>
+__global__ void k_gather_delta(const T *cur, const T *delta, double *dst, int np, int ey, int ez, int l0, int ny, int nzp) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    const int p = blockIdx.z;
+    if (k >= ez || j >= ey || p >= np) return;
+    const long long d = ((long long)(l0 + p) * ny + j) * nzp + k;
+    dst[((long long)p * ey + j) * ez + k] = (double)cur[d] - (double)delta[d];
 }
 
 // ---------------------------------------------------------------------------------------

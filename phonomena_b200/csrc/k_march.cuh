@@ -459,6 +459,7 @@ k_step_march(const __grid_constant__ MarchMaps tm, StepArgs<typename A::T> p, Ma
             mbar_wait(bar_fullO + (it % NSO) * 8, (uint32_t)(((it - 1) / NSO) & 1));   // planes 1, 2, ... use the ring
             const T *const oC = reinterpret_cast<const T *>(sm + C_::OFF_O + (it % NSO) * C_::OSTAGE) + (r - 1) * TZ + lane * V;   // u_old(n)
             PV ox, oy, oz;
+            PV dx, dy, dz;                            // COMP: new increments (stored in place of u_old)
             {   // (5) ux
                 const PV t6S = vec(xb + 2 * XCE + xS), uo = vec(oC);
 #pragma unroll
@@ -469,7 +470,8 @@ k_step_march(const __grid_constant__ MarchMaps tm, StepArgs<typename A::T> p, Ma
                     const T acc = A::add(A::add(A::scl(A::sub(t1n[e], t1c[e]), k0 ? g.fdx0 : sfx_n),
                                                 A::scl(A::sub(t6[e], t6S.v[e]), k0 ? g.sdy0 : ssy)),
                                          A::scl(A::sub(t5[e], t5w), zs.v[e]));
-                    ox.v[e] = advance<A>(uxc.v[e], uo.v[e], c[CLS_RX], acc);
+                    if constexpr (A::COMP) { dx.v[e] = uo.v[e] + c[CLS_RX] * acc; ox.v[e] = uxc.v[e] + dx.v[e]; }
+                    else ox.v[e] = advance<A>(uxc.v[e], uo.v[e], c[CLS_RX], acc);
                 }
             }
             {   // (6) uy
@@ -482,7 +484,8 @@ k_step_march(const __grid_constant__ MarchMaps tm, StepArgs<typename A::T> p, Ma
                     const T acc = A::add(A::add(A::scl(A::sub(t6[e], t6m[e]), k0 ? g.sdx0 : ssx_m),
                                                 A::scl(A::sub(t2N.v[e], t2c[e]), k0 ? g.fdy0 : sfy)),
                                          A::scl(A::sub(t4[e], t4w), zs.v[e]));
-                    oy.v[e] = advance<A>(uyc.v[e], uo.v[e], c[CLS_RY], acc);
+                    if constexpr (A::COMP) { dy.v[e] = uo.v[e] + c[CLS_RY] * acc; oy.v[e] = uyc.v[e] + dy.v[e]; }
+                    else oy.v[e] = advance<A>(uyc.v[e], uo.v[e], c[CLS_RY], acc);
                 }
             }
             {   // (7) uz   (k = 0: "+ T3[..,1] - T3[..,0]/fdz[0]", T3[..,1] NOT divided, App. B #3)
@@ -495,7 +498,8 @@ k_step_march(const __grid_constant__ MarchMaps tm, StepArgs<typename A::T> p, Ma
                     const T acc = A::add(A::add(A::scl(A::sub(t5[e], t5m[e]), k0 ? g.sdx0 : ssx_m),
                                                 A::scl(A::sub(t4[e], t4S.v[e]), k0 ? g.sdy0 : ssy)),
                                          A::scl(A::sub(t3u, t3c[e]), k0 ? (T)1 : zf.v[e]));
-                    oz.v[e] = advance<A>(uzc.v[e], uo.v[e], c[CLS_RZ], acc);
+                    if constexpr (A::COMP) { dz.v[e] = uo.v[e] + c[CLS_RZ] * acc; oz.v[e] = uzc.v[e] + dz.v[e]; }
+                    else oz.v[e] = advance<A>(uzc.v[e], uo.v[e], c[CLS_RZ], acc);
                 }
             }
             // i = 0: uy, uz keep u_new == u (App. B #9); uz(0, j, 0) is the pre-source value
@@ -503,6 +507,17 @@ k_step_march(const __grid_constant__ MarchMaps tm, StepArgs<typename A::T> p, Ma
                 oy = uyc;
                 oz = uzc;
                 if (k0c && p.line_save) oz.v[0] = p.line_save[j];
+                if constexpr (A::COMP) {      // keep delta = u_new - u here too (only matters for reading u_old back)
+#pragma unroll
+                    for (int e = 0; e < V; ++e) { dy.v[e] = (T)0; dz.v[e] = oz.v[e] - uzc.v[e]; }
+                }
+            }
+            if constexpr (A::COMP) {
+                if (in_box) {     // the u_old tile of this plane was read by TMA before: in-place update of delta
+                    *reinterpret_cast<PV *>(p.old.ux + off) = dx;
+                    *reinterpret_cast<PV *>(p.old.uy + off) = dy;
+                    *reinterpret_cast<PV *>(p.old.uz + off) = dz;
+                }
             }
             if (in_box) {
                 *reinterpret_cast<PV *>(p.nw.ux + off) = ox;

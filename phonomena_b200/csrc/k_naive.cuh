@@ -42,7 +42,13 @@ __device__ __forceinline__ void naive_cell(const StepArgs<typename A::T> &p, con
         const T acc = A::add(A::add(A::scl(dA, k0 ? g.fdx0 : g.fdx[i]), A::scl(dB, k0 ? g.sdy0 : g.sdy[j - 1])),
                              A::scl(dC, k0 ? g.sdz0 : g.sdz[k - 1]));
         const T rinv = ev.coef(i, j, k, CLS_RX);
-        p.nw.ux[c] = advance<A>(p.cur.ux[c], p.old.ux[c], rinv, acc);
+        if constexpr (A::COMP) {
+            const T dn = p.old.ux[c] + rinv * acc;      // p.old holds delta
+            p.old.ux[c] = dn;
+            p.nw.ux[c] = p.cur.ux[c] + dn;
+        } else {
+            p.nw.ux[c] = advance<A>(p.cur.ux[c], p.old.ux[c], rinv, acc);
+        }
     }
     // ---- uy: 1<=i<=nx-2, 0<=j<=ny-2 -------------------------------------------------------
     if (i >= 1 && i <= g.nx - 2 && j <= g.ny - 2) {
@@ -55,7 +61,13 @@ __device__ __forceinline__ void naive_cell(const StepArgs<typename A::T> &p, con
         const T acc = A::add(A::add(A::scl(dA, k0 ? g.sdx0 : g.sdx[i - 1]), A::scl(dB, k0 ? g.fdy0 : g.fdy[j])),
                              A::scl(dC, k0 ? g.sdz0 : g.sdz[k - 1]));
         const T rinv = ev.coef(i, j, k, CLS_RY);
-        p.nw.uy[c] = advance<A>(p.cur.uy[c], p.old.uy[c], rinv, acc);
+        if constexpr (A::COMP) {
+            const T dn = p.old.uy[c] + rinv * acc;      // p.old holds delta
+            p.old.uy[c] = dn;
+            p.nw.uy[c] = p.cur.uy[c] + dn;
+        } else {
+            p.nw.uy[c] = advance<A>(p.cur.uy[c], p.old.uy[c], rinv, acc);
+        }
     }
     // ---- uz: 1<=i<=nx-2, 1<=j<=ny-2 -------------------------------------------------------
     if (i >= 1 && i <= g.nx - 2 && j >= 1 && j <= g.ny - 2) {
@@ -74,12 +86,22 @@ __device__ __forceinline__ void naive_cell(const StepArgs<typename A::T> &p, con
             acc = A::add(A::add(sA, sB), A::scl(A::sub(a3, b3), g.fdz[k]));
         }
         const T rinv = ev.coef(i, j, k, CLS_RZ);
-        p.nw.uz[c] = advance<A>(p.cur.uz[c], p.old.uz[c], rinv, acc);
+        if constexpr (A::COMP) {
+            const T dn = p.old.uz[c] + rinv * acc;      // p.old holds delta
+            p.old.uz[c] = dn;
+            p.nw.uz[c] = p.cur.uz[c] + dn;
+        } else {
+            p.nw.uz[c] = advance<A>(p.cur.uz[c], p.old.uz[c], rinv, acc);
+        }
     }
     // ---- i = 0: uy, uz are never written by the physics; keep u_new == u (App. B #9) ------
     if (i == 0) {
         if (j <= g.ny - 2) p.nw.uy[c] = p.cur.uy[c];
         p.nw.uz[c] = (k0 && p.line_save) ? p.line_save[j] : p.cur.uz[c];
+        if constexpr (A::COMP) {      // keep delta = u_new - u here too (only matters for reading u_old back)
+            if (j <= g.ny - 2) p.old.uy[c] = (T)0;
+            p.old.uz[c] = p.nw.uz[c] - p.cur.uz[c];
+        }
     }
 }
 

@@ -224,9 +224,12 @@ struct Engine : IEngine {
         return g;
     }
     Fld<T> fld(int b) const { return Fld<T>{(T *)c->buf[b][0], (T *)c->buf[b][1], (T *)c->buf[b][2]}; }
+    // plain state: three buffers rotate (old <- cur <- new).  Compensated state (PHB_COMP): buffers 0 / 1
+    // ping-pong u, buffer 2 holds delta = u - u_old and is updated in place.
+    bool comp() const { return c->cfg.arith == PHB_COMP; }
     int b_cur() const { return c->cur; }
-    int b_old() const { return (c->cur + 2) % 3; }
-    int b_new() const { return (c->cur + 1) % 3; }
+    int b_old() const { return comp() ? 2 : (c->cur + 2) % 3; }
+    int b_new() const { return comp() ? 1 - c->cur : (c->cur + 1) % 3; }
 
     int set_spacing(const double *fdx, const double *fdy, const double *fdz, const double *sdx, const double *sdy,
                     const double *sdz) override {
@@ -350,11 +353,15 @@ struct Engine : IEngine {
             double *tmp = nullptr;
             CU(cudaMalloc(&tmp, bytes));
             dim3 bl = block_for(ez), g = grid3(ez, ey, np, bl);
+            const bool as_delta = this->comp() && which == PHB_OLD;   // the slot holds u - u_old (set PHB_CUR first)
+            const T *ucur = (const T *)c->buf[b_cur()][comp];
             if (to_dev) {
                 CU(cudaMemcpyAsync(tmp, h[comp], bytes, cudaMemcpyHostToDevice, c->st));
-                k_scatter<T><<<g, bl, 0, c->st>>>(tmp, (T *)c->buf[b][comp], np, ey, ez, 1, c->cfg.ny, c->nzp);
+                if (as_delta) k_scatter_delta<T><<<g, bl, 0, c->st>>>(tmp, ucur, (T *)c->buf[b][comp], np, ey, ez, 1, c->cfg.ny, c->nzp);
+                else k_scatter<T><<<g, bl, 0, c->st>>>(tmp, (T *)c->buf[b][comp], np, ey, ez, 1, c->cfg.ny, c->nzp);
             } else {
-                k_gather<T><<<g, bl, 0, c->st>>>((const T *)c->buf[b][comp], tmp, np, ey, ez, 1, c->cfg.ny, c->nzp);
+                if (as_delta) k_gather_delta<T><<<g, bl, 0, c->st>>>(ucur, (const T *)c->buf[b][comp], tmp, np, ey, ez, 1, c->cfg.ny, c->nzp);
+                else k_gather<T><<<g, bl, 0, c->st>>>((const T *)c->buf[b][comp], tmp, np, ey, ez, 1, c->cfg.ny, c->nzp);
                 CU(cudaMemcpyAsync(h[comp], tmp, bytes, cudaMemcpyDeviceToHost, c->st));
             }
             c->launches++;
@@ -371,6 +378,7 @@ struct Engine : IEngine {
     int dispatch(F &&f) {
         if (!c->code || !c->tab) return fail("material not set (table + ids)");
         if (c->cfg.arith == PHB_EXACT) return f.template operator()<Ar<T, true>>();
+        if (c->cfg.arith == PHB_COMP) return f.template operator()<Ar<T, false, true>>();
         return f.template operator()<Ar<T, false>>();
     }
 
@@ -510,7 +518,7 @@ struct Engine : IEngine {
             return 0;
         }
         for (int b = 0; b < 3; ++b) {
-            const int bo = (b + 2) % 3;
+            const int bo = comp() ? 2 : (b + 2) % 3;
             c->mm[b].u = cur[b];
             c->mm[b].o = old[bo];
             c->mm[b].c = cls;
@@ -523,7 +531,7 @@ struct Engine : IEngine {
 
     AbcArgs<T> abc_args(int ib, int ie) {
         AbcArgs<T> a;
-        a.g = geo(); a.cur = fld(b_cur()); a.nw = fld(b_new());
+        a.g = geo(); a.cur = fld(b_cur()); a.nw = fld(b_new()); a.dl = fld(b_old());
         a.clx = (T)c->abc[0]; a.ctx = (T)c->abc[1]; a.cly0 = (T)c->abc[2]; a.cty0 = (T)c->abc[3];
         a.cly1 = (T)c->abc[4]; a.cty1 = (T)c->abc[5]; a.clz = (T)c->abc[6]; a.ctz = (T)c->abc[7];
         a.i_begin = ib; a.i_end = ie;
@@ -533,6 +541,7 @@ struct Engine : IEngine {
         AbcArgs<T> a = abc_args(0, 0);
         dim3 bl = block_for(c->cfg.nz), gr = grid3(c->cfg.nz, c->cfg.ny, 1, bl);
         if (c->cfg.arith == PHB_EXACT) k_abc_x<Ar<T, true>><<<gr, bl, 0, c->st>>>(a);
+        else if (comp()) k_abc_x<Ar<T, false, true>><<<gr, bl, 0, c->st>>>(a);
         else k_abc_x<Ar<T, false>><<<gr, bl, 0, c->st>>>(a);
         c->launches++;
         CU(cudaGetLastError());
@@ -545,11 +554,13 @@ struct Engine : IEngine {
             dim3 bl = block_for(c->cfg.nz), gr = grid3(c->cfg.nz, ie - ib, 1, bl);
             gr.z = 2;
             if (c->cfg.arith == PHB_EXACT) k_abc_y<Ar<T, true>><<<gr, bl, 0, c->st>>>(a);
+            else if (comp()) k_abc_y<Ar<T, false, true>><<<gr, bl, 0, c->st>>>(a);
             else k_abc_y<Ar<T, false>><<<gr, bl, 0, c->st>>>(a);
         }
         {
             dim3 bl(32, 8, 1), gr = grid3(c->cfg.ny, ie - ib, 1, bl);
             if (c->cfg.arith == PHB_EXACT) k_abc_z<Ar<T, true>><<<gr, bl, 0, c->st>>>(a);
+            else if (comp()) k_abc_z<Ar<T, false, true>><<<gr, bl, 0, c->st>>>(a);
             else k_abc_z<Ar<T, false>><<<gr, bl, 0, c->st>>>(a);
         }
         c->launches += 2;
@@ -707,7 +718,7 @@ int phb_create(const phb_cfg *cfg, phb_ctx **out) {
     if (cfg->nx < 4 || cfg->ny < 4 || cfg->nz < 4) return fail("grid must be at least 4 points per axis (got %d x %d x %d)", cfg->nx, cfg->ny, cfg->nz);
     if (cfg->x0 < 0 || cfg->nxl < 1 || cfg->x0 + cfg->nxl > cfg->nx) return fail("bad slab [%d, %d) of %d", cfg->x0, cfg->x0 + cfg->nxl, cfg->nx);
     if (cfg->dtype != PHB_F32 && cfg->dtype != PHB_F64) return fail("bad dtype %d", cfg->dtype);
-    if (cfg->arith != PHB_FAST && cfg->arith != PHB_EXACT) return fail("bad arith %d", cfg->arith);
+    if (cfg->arith != PHB_FAST && cfg->arith != PHB_EXACT && cfg->arith != PHB_COMP) return fail("bad arith %d", cfg->arith);
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)

@@ -43,7 +43,8 @@ logger = logging.getLogger(__name__)
 # (solver_numba.py:8-13,22).  All values are JSON-serialisable (common.saveSettings dumps them).
 cfg = {
     "precision": "fp64",        # "fp64" | "fp32": storage and arithmetic type on the device
-    "arith": "fast",            # "fast" (<=1e-12 of the reference in fp64) | "exact" (bit-identical, slower)
+    "arith": "fast",            # "fast" (<=1e-12 of the reference in fp64) | "exact" (bit-identical, slower) |
+                                # "compensated" (state u, u-u_old: 4-8x less fp32 round-off drift on long runs)
     "device": 0,                # CUDA device ordinal (one process per GPU; slabs via torchrun, see slab_from_env)
     "record": "surface",        # "surface": uz (and ux, uy) at z-index 0 per step | "full": whole fields | "off"
     "record_every": 1,

@@ -101,3 +101,17 @@ def test_random_fields_nonuniform_xyz_vs_oracle(kernel):
                 assert np.array_equal(got, getattr(o, key)), (n, key)
         for got, key in zip(e.get_stress(which=1), ("T1", "T2", "T3", "T4", "T5", "T6")):
             assert np.array_equal(got, getattr(o, key)), key
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("name", H.golden_names())
+def test_compensated_state_within_tolerance(name, kernel):
+    """PHB_COMP (state u, delta): same step algebraically -> fp64 <= 1e-12, fp32 <= 1e-5 of the reference;
+    `old` fields read back as u - delta."""
+    d = H.load_golden(name)
+    for dtype, tol in (("f64", TOL_F64_FAST), ("f32", TOL_F32)):
+        with H.engine_from_golden(d, dtype=dtype, arith="comp", kernel=kernel) as e:
+            e.run(d["steps"])
+            got, old = e.get_fields(), e.get_fields(which=1)
+        assert H.rel_l2(got, [d["ux"], d["uy"], d["uz"]]) <= tol, (name, dtype)
+        assert H.rel_l2(old, [d["ux_old"], d["uy_old"], d["uz_old"]]) <= 10 * tol, (name, dtype)
