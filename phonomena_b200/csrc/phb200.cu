@@ -466,9 +466,12 @@ struct Engine : IEngine {
                 else if (c->mR == 16 && c->mNST == 3) r = launch_march_cfg<A, 16, 3>(p, m, mp, ch, c->st);
                 else if (c->mR == 8 && c->mNST == 4) r = launch_march_cfg<A, 8, 4>(p, m, mp, ch, c->st);
                 if (r == -2) return fail("no marching-kernel instantiation for R=%d NST=%d", c->mR, c->mNST);
-                if (r < 0) return fail("marching kernel needs more shared memory than the device allows (%d classes)", c->ncls);
-                c->launches += r;
-            } else {
+                if (r < 0 && (c->cfg.kernel == PHB_KERNEL_MARCH || c->halo == 2))
+                    return fail("marching kernel needs more shared memory than the device allows (%d classes)", c->ncls);
+                if (r >= 0) { c->launches += r; return 0; }
+                c->maps_ok = false;      // kernel = auto: too many stencil classes for the shared-memory table -> naive kernel
+            }
+            {
                 dim3 bl = block_for(c->cfg.nz), gr = grid3(c->cfg.nz, c->cfg.ny, ie - ib, bl);
                 k_step_naive<A, MatCls<T>><<<gr, bl, 0, c->st>>>(p, m);
                 c->launches++;

@@ -135,3 +135,33 @@ def test_c_abi_error_behaviour():
         with pytest.raises(_lib.PhbError, match="shape"):
             e.set_fields(np.zeros((8, 8, 8)), None, None)
         assert e.steps_done == 2 and e.launch_count > 0
+
+
+def test_random_two_material_medium_every_stencil_class():
+    """Per-cell random material (not cylinders): exercises (nearly) all 2^7 stencil classes plus their
+    boundary variants; uploaded with phb_set_material_ids.  EXACT arithmetic vs the C oracle, bit for bit,
+    with kernel = auto (marching kernel, or the naive one if the class table outgrows shared memory)."""
+    from phonomena_b200 import _lib, hostmath as hm
+    from oracle import fdtd_c
+    rng = np.random.default_rng(11)
+    case = _case((20, 18, 70), rng)
+    nx, ny, nz = case.shape
+    ids = (rng.random((nx, ny, nz)) < 0.4).astype(np.uint8)
+    ids[:3, :3, :3] = 0            # corner cell primary (Mur coefficients)
+    steps = 9
+    o = fdtd_c.COracle(case.x, case.y, case.z, ids, [case.prim_c, case.sec_c], [case.prim_p, case.sec_p], case.dt,
+                       wave="ricker", wave_args=case.wave_args)
+    o.run(steps)
+    for kernel in ("auto", "naive"):
+        e = _lib.Engine(nx, ny, nz, case.dt, dtype="f64", arith="exact", kernel=kernel)
+        e.set_spacing(*case.sp)
+        e.set_material_table([case.prim_c, case.sec_c], [case.prim_p, case.sec_p])
+        e.set_material_ids(ids)
+        assert np.array_equal(e.get_material_ids(), ids)
+        e.set_abc(hm.abc_coefficients(case.prim_c, case.prim_p, case.dt, *case.sp))
+        e.set_source_table(hm.source_table("ricker", steps, case.dt, case.wave_args))
+        e.run(steps)
+        for a, k in zip(e.get_fields(), ("ux", "uy", "uz")):
+            assert np.array_equal(a, getattr(o, k)), (kernel, k)
+        e.close()
+    o.close()

@@ -88,3 +88,28 @@ def test_h5lite_roundtrip_multilevel_btree(tmp_path):
     assert np.array_equal(r.read("density"), P)
     for t in (0, 63, 64, 4095, 4096, 4999):
         assert np.array_equal(r.read("uz", frame=t), frames[t])
+
+
+def test_spectrum_matches_reference_formula(tmp_path):
+    """phonomena_b200.analysis.spectrum on an h5lite file == the reference's expression
+    (simulation/analysis.py:59-88) evaluated with NumPy on the same data."""
+    from phonomena_b200 import analysis
+    from phonomena_b200.h5lite import H5Writer
+    rng = np.random.default_rng(2)
+    nx, ny, N, dt = 9, 5, 64, 2.5e-5
+    data = rng.standard_normal((nx, ny, 1, N))
+    x = np.cumsum(rng.uniform(0.5, 1.5, nx))
+    p = str(tmp_path / "s.h5")
+    with H5Writer(p) as w:
+        w.attrs.update({"x": x, "fdx": np.diff(x).reshape(-1, 1, 1), "dt": dt, "steps": N})
+        d = w.create_chunked("uz", (nx, ny, 1, N))
+        for t in range(N):
+            w.write_frame(d, t, data[..., t])
+    xs, f, dft = analysis.spectrum(p, "uz", 0, 3)
+    win = np.hanning(N)
+    ref = np.abs(np.fft.fft2(data[:, 3, 0, :] * win, norm="ortho"))[:, :N // 2]
+    assert np.array_equal(xs, x) and np.array_equal(f, np.fft.fftfreq(N, d=dt)[:N // 2]) and np.allclose(dft, ref, rtol=1e-13, atol=0)
+    _, _, d1 = analysis.spectrum(p, "uz", 0, 3, x_index=4)
+    assert np.allclose(d1, np.abs(np.fft.fft(data[4, 3, 0, :] * win, norm="ortho"))[:N // 2], rtol=1e-13, atol=0)
+    out, idx = analysis.trim_trailing_zeros(d1.copy())
+    assert out.size == len(idx) <= d1.size
