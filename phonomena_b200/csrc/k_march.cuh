@@ -8,17 +8,22 @@
 //    plays in the usual 2.5-D blocking.  A block owns a (TY rows x 32*V cells) tile of the
 //    (y, z) plane and a chunk of x-planes; warp r of the block is row j0-1+r, so the first
 //    and last warps are the y-halo rows (they only compute stresses).
-//  * EVERY input arrives by TMA (cp.async.bulk.tensor.3d -> UTMALDG) into an NST-stage shared
-//    ring, one stage per x-plane: the three u_cur tiles with a 16-byte halo vector on each
-//    side in z and a halo row on each side in y, the three u_old tiles (no halo) and the
-//    1-byte stencil-class tile.  Out-of-range rows / columns / planes are zero-filled by the
-//    TMA unit, so there is no load-side boundary code and no global load instruction in the
-//    plane loop.  Lane 0 of warp 0 is the producer; `full[s]` / `empty[s]` mbarriers gate
-//    the ring.
+//  * EVERY input arrives by TMA (cp.async.bulk.tensor.4d / .3d -> UTMALDG): per x-plane one stage of
+//    an NST-deep shared ring gets the three u_cur tiles in ONE 4-D transfer (z, y, plane,
+//    component; 16-byte halo vector on each side in z, halo row on each side in y) plus the
+//    1-byte stencil-class tile; the three u_old tiles (no halo, needed only late in the
+//    iteration) use their own 2-deep ring, again one 4-D transfer.  Out-of-range rows / columns /
+//    planes are zero-filled by the TMA unit, so there is no load-side boundary code and no global
+//    load instruction in the plane loop.  `full[s]` mbarriers signal arrival; `done[s]` (bar_empty,
+//    one arrival per warp) releases a stage.  There is no producer warp: the lane whose arrival
+//    completes `done[s]` finds it complete, claims the next plane with a shared-memory CAS and
+//    issues its TMA loads.  Every issued TMA is waited for by some warp before the block exits.
 //  * There is NO block-wide barrier in the plane loop.  Per plane a row-warp publishes its
 //    T2/T4/T6 (the stresses its y-neighbours need) into a double-buffered exchange tile and
-//    signals the `pub[r][parity]` mbarrier; it then waits only for its two neighbours.
-//    Warps drift by up to one plane, which absorbs memory-latency jitter.
+//    arrives on its two neighbours' `nb[r][parity]` mbarriers; it then waits on its own, once.
+//    The halo rows (first / last warp) compute only what their one neighbour reads.
+//  * Multi-GPU (template PUSH): the first / last owned plane of u_new is also stored into the
+//    neighbours' ghost planes through CUDA-IPC peer pointers (NVLink), see phb200.cu step().
 //  * Per plane a thread keeps in registers, per cell: u(n) (own position), the normal stresses
 //    T1..T3(n) and the shear stresses T5(n-1), T6(n-1) carried from the previous plane.
 //    z-neighbours come from warp shuffles; the two edge lanes rebuild the three halo stresses
