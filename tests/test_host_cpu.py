@@ -113,3 +113,20 @@ def test_spectrum_matches_reference_formula(tmp_path):
     assert np.allclose(d1, np.abs(np.fft.fft(data[4, 3, 0, :] * win, norm="ortho"))[:N // 2], rtol=1e-13, atol=0)
     out, idx = analysis.trim_trailing_zeros(d1.copy())
     assert out.size == len(idx) <= d1.size
+
+
+def test_bench_reference_arm_contract_line():
+    """`bench.py --impl reference` (CPU only): one JSON line with the contract's keys."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in line, k
+    assert line["impl"] == "reference" and line["metric"] == "Gcell-updates/s" and line["unit"] == "Gcell/s"
+    assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"] and "workload" in line["config"]
