@@ -637,7 +637,10 @@ inline int launch_march_cfg(const StepArgs<typename A::T> &p, const MatCls<typen
         if (p.push_lo[0] || p.push_hi[0]) return launch_march_cfg<A, R, NST, true>(p, m, maps, chunks, st);
     }
     auto kern = k_step_march<A, R, NST, PUSH>;
-    static size_t attr_bytes = 0;   // per template instantiation
+    static size_t attr_by_dev[64] = {};   // per template instantiation and device (the attribute is per device)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    size_t &attr_bytes = attr_by_dev[dev & 63];
     const int np = p.i_end - p.i_begin;
     if (np <= 0) return 0;
     if (chunks < 1) chunks = 1;
