@@ -163,6 +163,30 @@ int phb_record_next(phb_ctx *ctx, const double **frame, int64_t *tt, int32_t tim
 int phb_record_release(phb_ctx *ctx);
 int phb_record_frame_doubles(phb_ctx *ctx, int64_t *n);
 
+/* line probes and on-device spectra.
+ * replaces: simulation/analysis.py:59-66 -- the reference re-reads the (x, t) matrix
+ * u[:, y, z, :] from the HDF5 file; a probe keeps it in device memory while the run goes on.
+ * phb_probe_add: probe component comp (0 ux, 1 uy, 2 uz) on the line (:, j, k), room for
+ * `capacity` samples.  One sample is taken after every step tt with tt % record_every == 0 --
+ * the same instants as the recorded frames (base_solver.py:256-260: the state AFTER time_step).
+ * Rows are this slab's planes on which the component exists (ux has Nx-1 planes). */
+int phb_probe_add(phb_ctx *ctx, int32_t comp, int32_t j, int32_t k, int64_t capacity, int32_t *id);
+int phb_probe_shape(phb_ctx *ctx, int32_t id, int64_t *rows, int64_t *frames);
+/* out[row][frame], float64 */
+int phb_probe_read(phb_ctx *ctx, int32_t id, double *out);
+/* replaces: simulation/analysis.py:67-86 (np.fft.fft / np.fft.fft2 of the windowed matrix).
+ * window: the `frames` weights (np.hanning(frames) in the reference); nf: frequencies kept
+ * (frames // 2).  Outputs are UNNORMALISED complex sums; the caller applies norm="ortho" and abs.
+ * phb_probe_dft_t : out[(row - row0)][kt] = sum_t u[row][t] w[t] exp(-2 pi i kt t / frames),
+ *                   rows row0 .. row0 + nrows - 1 of this slab.
+ * phb_probe_dft_xt: out[kx][kt] = sum_{rows of this slab} (the above)[row][kt] *
+ *                   exp(-2 pi i kx (x0 + row) / nx_total): this slab's share of the 2-D
+ *                   transform over nx_total rows; slabs add. */
+int phb_probe_dft_t(phb_ctx *ctx, int32_t id, const double *window, int64_t nf, int64_t row0, int64_t nrows,
+                    double *out_re, double *out_im);
+int phb_probe_dft_xt(phb_ctx *ctx, int32_t id, const double *window, int64_t nf, int64_t nx_total,
+                     double *out_re, double *out_im);
+
 #ifdef __cplusplus
 }
 #endif

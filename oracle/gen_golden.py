@@ -117,6 +117,38 @@ def case_custom(name, size, max_d, min_d, incl, steps, snaps, wave, wave_args, c
     _pack(name, s, fr, steps, courant)
 
 
+def case_spectrum(name, path, steps, y_index, x_index):
+    """The reference's own post-processing (simulation/analysis.py:44-96) on the reference solver's
+    own frames: run `steps` steps, keep the (x, t) lines a probe would keep (frame tt = the state
+    after time_step of step tt, base_solver.py:256-260), hand them to `spectrum` through the
+    in-memory h5py stand-in and store lines + answers."""
+    common = refshim.install()
+    common.findSolvers()
+    cfg, g, m = common.loadSettings(path)
+    s = refshim.default_solver()
+    s.cfg.update(dict(cfg["simulation"]["cfg"]))
+    s.cfg["write_mode"] = "off"
+    s.init(g, m, steps)
+    wave_fn = {"sin": s.update_sin, "ricker": s.update_ricker}[s.cfg["wave"]]
+    full = {k: np.zeros(getattr(s.g, k).shape + (steps,)) for k in ("ux", "uy", "uz")}
+    for tt in range(steps):
+        s.g.uz[0, :, 0] = wave_fn(tt=tt, **s.cfg["wave_args"])
+        s.update_T(); s.update_T_BC(); s.update_u(); s.update_u_BC(); s.time_step()
+        for k in full:
+            full[k][..., tt] = getattr(s.g, k)
+    import h5py                                   # the stand-in installed by refshim
+    from simulation import analysis as ranalysis
+    f = h5py.File.in_memory(full, {"x": s.g.x, "fdx": s.g.fdx, "dt": s.m.dt})
+    d = dict(steps=steps, dt=s.m.dt, y_index=y_index, x_index=x_index, x=s.g.x, fdx=s.g.fdx[:, 0, 0])
+    for u_id in ("ux", "uz"):
+        d["line_" + u_id] = full[u_id][:, y_index, 0, :]
+        for tag, xi in (("2d", None), ("1d", x_index)):
+            x, fr, dft = ranalysis.spectrum(f, u_id, z_index=0, y_index=y_index, x_index=xi)
+            d["x_%s" % u_id], d["f"], d["dft_%s_%s" % (u_id, tag)] = x, fr, dft
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+    print("wrote", name, {k: np.shape(v) for k, v in d.items()})
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = refshim.REF_ROOT
@@ -135,6 +167,7 @@ def main():
     case_custom("crystal_48x32x12", (47, 31, 11), (1, 1, 1), 1,
                 [(8.0 + 16 * a, 8.0 + 16 * b, 11.0, 4.0) for a in range(3) for b in range(2)][:5],
                 80, (1, 80), "sin", {"f": 100})
+    case_spectrum("spectrum_default_json_128", os.path.join(ref, "data", "default.json"), 128, 10, 5)
 
 
 if __name__ == "__main__":

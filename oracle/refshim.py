@@ -7,7 +7,8 @@ product imports it.
 
 Three shims, no edits to the reference:
   1. stub ``PyQt5.QtCore`` (``gui/worker.py`` only needs QObject/QRunnable/pyqtSignal/pyqtSlot)
-  2. stub ``h5py`` (the oracle always runs with ``write_mode='off'``)
+  2. stub ``h5py`` (the solver always runs with ``write_mode='off'``; ``h5py.File.in_memory`` feeds
+     simulation/analysis.py with arrays)
   3. ``numpy.float = float`` (removed in NumPy >= 1.24, used at grid.py:258,301)
 """
 import os
@@ -58,10 +59,40 @@ def install():
     if "h5py" not in sys.modules:
         h5 = types.ModuleType("h5py")
 
-        def _file(*a, **k):
-            raise RuntimeError("h5py is stubbed: run the reference with write_mode='off'")
+        class _Dataset:
+            """What simulation/analysis.py touches of an h5py dataset: != None, .shape, slicing."""
 
-        h5.File = _file
+            def __init__(self, a):
+                self._a = np.asarray(a)
+                self.shape = self._a.shape
+
+            def __ne__(self, other):
+                return True
+
+            def __getitem__(self, idx):
+                return self._a[idx]
+
+        class File:
+            """In-memory stand-in: real files are refused (the reference solver runs with
+            write_mode='off'); ``File.in_memory(datasets, attrs)`` feeds simulation/analysis.py."""
+
+            def __init__(self, *a, **k):
+                raise RuntimeError("h5py is stubbed: run the reference with write_mode='off'")
+
+            @classmethod
+            def in_memory(cls, datasets, attrs):
+                f = cls.__new__(cls)
+                f._d = {k: _Dataset(v) for k, v in datasets.items()}
+                f.attrs = dict(attrs)
+                return f
+
+            def get(self, name):
+                return self._d.get(name)
+
+            def close(self):
+                pass
+
+        h5.File = File
         h5.__stub__ = True
         sys.modules["h5py"] = h5
     pkg = os.path.join(REF_ROOT, "phonomena")

@@ -26,7 +26,7 @@ SYMBOLS = (
     "phb_get_material_ids", "phb_set_abc", "phb_set_source_table", "phb_set_fields", "phb_get_fields",
     "phb_get_stress", "phb_run", "phb_sync", "phb_run_timed", "phb_steps_done", "phb_launch_count",
     "phb_info", "phb_profile", "phb_comm_unique_id", "phb_comm_init", "phb_p2p_export", "phb_p2p_import", "phb_record_next", "phb_record_release",
-    "phb_record_frame_doubles",
+    "phb_record_frame_doubles", "phb_probe_add", "phb_probe_shape", "phb_probe_read", "phb_probe_dft_t", "phb_probe_dft_xt",
 )
 
 
@@ -89,6 +89,11 @@ def load_library(path=None):
     lib.phb_record_next.argtypes = [vp, C.POINTER(dp), C.POINTER(C.c_int64), C.c_int32]
     lib.phb_record_release.argtypes = [vp]
     lib.phb_record_frame_doubles.argtypes = [vp, C.POINTER(C.c_int64)]
+    lib.phb_probe_add.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.POINTER(C.c_int32)]
+    lib.phb_probe_shape.argtypes = [vp, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    lib.phb_probe_read.argtypes = [vp, C.c_int32, dp]
+    lib.phb_probe_dft_t.argtypes = [vp, C.c_int32, dp, C.c_int64, C.c_int64, C.c_int64, dp, dp]
+    lib.phb_probe_dft_xt.argtypes = [vp, C.c_int32, dp, C.c_int64, C.c_int64, dp, dp]
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if name not in ("phb_last_error",):
@@ -352,3 +357,44 @@ class Engine:
 
     def record_release(self):
         _chk(self.lib, self.lib.phb_record_release(self._ctx))
+
+    # ---- line probes and on-device spectra (include/phb200.h "line probes") ----
+    def probe_add(self, comp, j, k, capacity):
+        """Keep u_comp[:, j, k] of every recorded step on the device; comp: 'ux'|'uy'|'uz' or 0..2."""
+        comp = {"ux": 0, "uy": 1, "uz": 2}.get(comp, comp)
+        pid = C.c_int32(-1)
+        _chk(self.lib, self.lib.phb_probe_add(self._ctx, int(comp), int(j), int(k), int(capacity), C.byref(pid)))
+        return pid.value
+
+    def probe_shape(self, pid):
+        rows, frames = C.c_int64(0), C.c_int64(0)
+        _chk(self.lib, self.lib.phb_probe_shape(self._ctx, int(pid), C.byref(rows), C.byref(frames)))
+        return rows.value, frames.value
+
+    def probe_read(self, pid):
+        """(rows, frames) float64: this slab's part of u[:, j, k, :]."""
+        rows, frames = self.probe_shape(pid)
+        out = np.zeros((rows, frames), np.float64)
+        _chk(self.lib, self.lib.phb_probe_read(self._ctx, int(pid), _dptr(out)))
+        return out
+
+    def probe_dft_t(self, pid, window, nf, row0=0, nrows=None):
+        """Unnormalised sum_t u[row, t] w[t] exp(-2 pi i k t / N) for k < nf: complex (nrows, nf)."""
+        rows, frames = self.probe_shape(pid)
+        nrows = rows - row0 if nrows is None else nrows
+        window = np.ascontiguousarray(window, np.float64)
+        if window.size != frames:
+            raise ValueError("window has %d weights, the probe holds %d frames" % (window.size, frames))
+        re, im = np.zeros((nrows, nf)), np.zeros((nrows, nf))
+        _chk(self.lib, self.lib.phb_probe_dft_t(self._ctx, int(pid), _dptr(window), int(nf), int(row0), int(nrows), _dptr(re), _dptr(im)))
+        return re + 1j * im
+
+    def probe_dft_xt(self, pid, window, nf, nx_total):
+        """This slab's share of the unnormalised 2-D (x, t) transform: complex (nx_total, nf); slabs add."""
+        _, frames = self.probe_shape(pid)
+        window = np.ascontiguousarray(window, np.float64)
+        if window.size != frames:
+            raise ValueError("window has %d weights, the probe holds %d frames" % (window.size, frames))
+        re, im = np.zeros((nx_total, nf)), np.zeros((nx_total, nf))
+        _chk(self.lib, self.lib.phb_probe_dft_xt(self._ctx, int(pid), _dptr(window), int(nf), int(nx_total), _dptr(re), _dptr(im)))
+        return re + 1j * im

@@ -22,6 +22,7 @@
 #include "fd_common.cuh"
 #include "k_boundary.cuh"
 #include "k_march.cuh"
+#include "k_probe.cuh"
 #include "k_naive.cuh"
 
 using namespace phb;
@@ -167,6 +168,9 @@ struct phb_ctx {
     size_t prof_used = 0;
     double prof_ms = 0;
     long long prof_n = 0;
+    // line probes (k_probe.cuh)
+    struct Probe { int comp, j, k, rows; long long cap, frames; double *trace; };
+    std::vector<Probe> probes;
     IEngine *eng = nullptr;
     std::mutex mu;
 };
@@ -702,6 +706,64 @@ static int record_frame(phb_ctx *c) {
 }
 
 // ------------------------------------------------------------------------------------------
+// line probes
+// ------------------------------------------------------------------------------------------
+template <class T> static inline const T *fld_comp(const Fld<T> &f, int comp) { return comp == 0 ? f.ux : comp == 1 ? f.uy : f.uz; }
+static int probe_sample(phb_ctx *c) {
+    for (auto &pr : c->probes) {
+        if (pr.rows <= 0) continue;
+        if (pr.frames >= pr.cap) return fail("probe is full (%lld samples)", pr.cap);
+        double *dst = pr.trace + pr.frames * pr.rows;
+        const int bl = 128, gr = (pr.rows + bl - 1) / bl;
+        if (c->cfg.dtype == PHB_F64) {
+            auto *e = static_cast<Engine<double> *>(c->eng);
+            k_probe_sample<double><<<gr, bl, 0, c->st>>>(e->geo(), fld_comp(e->fld(c->cur), pr.comp), pr.j, pr.k, pr.rows, dst);
+        } else {
+            auto *e = static_cast<Engine<float> *>(c->eng);
+            k_probe_sample<float><<<gr, bl, 0, c->st>>>(e->geo(), fld_comp(e->fld(c->cur), pr.comp), pr.j, pr.k, pr.rows, dst);
+        }
+        c->launches++;
+        pr.frames++;
+    }
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// windowed DFT along t of rows [row0, row0 + nrows) -> device A[nrows][nf]; the caller frees *A_out, *tw_out
+static int probe_dft_t_dev(phb_ctx *c, const phb_ctx::Probe &pr, const double *window, long long nf, long long row0,
+                           long long nrows, double2 **A_out) {
+    const long long n = pr.frames;
+    if (n < 1 || nf < 1 || nf > n) return fail("bad spectrum size: %lld frames, %lld frequencies", n, nf);
+    if (row0 < 0 || nrows < 0 || row0 + nrows > pr.rows) return fail("probe rows [%lld, %lld) outside [0, %d)", row0, row0 + nrows, pr.rows);
+    if (n >= (1LL << 30)) return fail("too many frames");
+    double *win = nullptr;
+    double2 *tw = nullptr, *A = nullptr;
+    CU(cudaMallocAsync((void **)&win, (size_t)n * sizeof(double), c->st));
+    CU(cudaMallocAsync((void **)&tw, (size_t)n * sizeof(double2), c->st));
+    CU(cudaMallocAsync((void **)&A, (size_t)std::max(1LL, nrows * nf) * sizeof(double2), c->st));
+    CU(cudaMemcpyAsync(win, window, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->st));
+    k_twiddle<<<(unsigned)((n + 255) / 256), 256, 0, c->st>>>(tw, (int)n);
+    if (nrows > 0) {
+        dim3 bl(32, 8), gr((unsigned)((nrows + 31) / 32), (unsigned)((nf + 7) / 8));
+        k_dft_t<<<gr, bl, 0, c->st>>>(pr.trace, pr.rows, (int)n, win, tw, (int)nf, (int)row0, (int)nrows, A);
+    }
+    c->launches += 2;
+    CU(cudaGetLastError());
+    CU(cudaFreeAsync(win, c->st));
+    CU(cudaFreeAsync(tw, c->st));
+    *A_out = A;
+    return 0;
+}
+
+static int split_to_host(phb_ctx *c, const double2 *dev, long long count, double *re, double *im) {
+    std::vector<double2> h((size_t)count);
+    CU(cudaMemcpyAsync(h.data(), dev, (size_t)count * sizeof(double2), cudaMemcpyDeviceToHost, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    for (long long q = 0; q < count; ++q) { re[q] = h[(size_t)q].x; im[q] = h[(size_t)q].y; }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------
 extern "C" {
@@ -806,6 +868,7 @@ int phb_destroy(phb_ctx *c) {
     for (auto &ev : c->stage_ev) cudaEventDestroy(ev);
     if (c->rst) { cudaStreamSynchronize(c->rst); cudaStreamDestroy(c->rst); }
     cudaFree(c->ring_dev);
+    for (auto &pr : c->probes) cudaFree(pr.trace);
     for (auto &pe : c->prof_ev) { cudaEventDestroy(pe.first); cudaEventDestroy(pe.second); }
     if (c->ev_edge) cudaEventDestroy(c->ev_edge);
     if (c->ev_comm) cudaEventDestroy(c->ev_comm);
@@ -975,7 +1038,10 @@ static int run_locked(phb_ctx *c, int64_t nsteps) {
     if (c->nranks > 1 && !c->comm && c->halo != 2) return fail("slab context without halo exchange: call phb_comm_init or phb_p2p_import");
     for (int64_t s = 0; s < nsteps; ++s) {
         OK(c->eng->step());
-        if (c->cfg.record_mask && (c->tt % c->cfg.record_every) == 0) OK(record_frame(c));
+        if ((c->tt % c->cfg.record_every) == 0) {
+            if (c->cfg.record_mask) OK(record_frame(c));
+            if (!c->probes.empty()) OK(probe_sample(c));
+        }
     }
     return 0;
 }
@@ -1141,6 +1207,77 @@ int phb_record_release(phb_ctx *c) {
     if (!c || !c->ring) return fail("recording not enabled");
     if (c->released.load() < c->consumed.load()) c->released.fetch_add(1);
     return 0;
+}
+
+int phb_probe_add(phb_ctx *c, int32_t comp, int32_t j, int32_t k, int64_t capacity, int32_t *id) {
+    ENTER(c);
+    if (!id) return fail("null argument");
+    if (comp < 0 || comp > 2) return fail("bad component %d", comp);
+    const int nyc = c->cfg.ny - (comp == 1), nzc = c->cfg.nz - (comp == 2), nxc = c->cfg.nx - (comp == 0);
+    if (j < 0 || j >= nyc || k < 0 || k >= nzc) return fail("probe line (%d, %d) outside the %d x %d field", j, k, nyc, nzc);
+    if (capacity < 1) return fail("bad probe capacity");
+    phb_ctx::Probe pr{};
+    pr.comp = comp; pr.j = j; pr.k = k;
+    pr.rows = std::max(0, std::min(c->cfg.x0 + c->cfg.nxl, nxc) - c->cfg.x0);
+    pr.cap = capacity; pr.frames = 0;
+    if (dmalloc(c, (void **)&pr.trace, (size_t)std::max(1LL, (long long)pr.rows * capacity) * sizeof(double), false)) return 1;
+    c->probes.push_back(pr);
+    *id = (int32_t)c->probes.size() - 1;
+    return 0;
+}
+#define PROBE(c, id) \
+    if ((id) < 0 || (size_t)(id) >= (c)->probes.size()) return fail("no probe %d", (int)(id)); \
+    const phb_ctx::Probe &pr = (c)->probes[(size_t)(id)]
+int phb_probe_shape(phb_ctx *c, int32_t id, int64_t *rows, int64_t *frames) {
+    ENTER(c);
+    PROBE(c, id);
+    if (rows) *rows = pr.rows;
+    if (frames) *frames = pr.frames;
+    return 0;
+}
+int phb_probe_read(phb_ctx *c, int32_t id, double *out) {
+    ENTER(c);
+    PROBE(c, id);
+    if (!out) return fail("null argument");
+    const long long n = pr.frames, rows = pr.rows;
+    if (n == 0 || rows == 0) return 0;
+    std::vector<double> h((size_t)(n * rows));
+    CU(cudaMemcpyAsync(h.data(), pr.trace, h.size() * sizeof(double), cudaMemcpyDeviceToHost, c->st));
+    CU(cudaStreamSynchronize(c->st));
+    for (long long t = 0; t < n; ++t)
+        for (long long p = 0; p < rows; ++p) out[p * n + t] = h[(size_t)(t * rows + p)];
+    return 0;
+}
+int phb_probe_dft_t(phb_ctx *c, int32_t id, const double *window, int64_t nf, int64_t row0, int64_t nrows,
+                    double *out_re, double *out_im) {
+    ENTER(c);
+    PROBE(c, id);
+    if (!window || !out_re || !out_im) return fail("null argument");
+    double2 *A = nullptr;
+    OK(probe_dft_t_dev(c, pr, window, nf, row0, nrows, &A));
+    int r = split_to_host(c, A, nrows * nf, out_re, out_im);
+    cudaFreeAsync(A, c->st);
+    return r;
+}
+int phb_probe_dft_xt(phb_ctx *c, int32_t id, const double *window, int64_t nf, int64_t nx_total,
+                     double *out_re, double *out_im) {
+    ENTER(c);
+    PROBE(c, id);
+    if (!window || !out_re || !out_im) return fail("null argument");
+    if (nx_total < 1 || nx_total >= (1LL << 30) || c->cfg.x0 + pr.rows > nx_total)
+        return fail("bad total row count %lld", (long long)nx_total);
+    double2 *A = nullptr, *F = nullptr, *twx = nullptr;
+    OK(probe_dft_t_dev(c, pr, window, nf, 0, pr.rows, &A));
+    CU(cudaMallocAsync((void **)&F, (size_t)(nx_total * nf) * sizeof(double2), c->st));
+    CU(cudaMallocAsync((void **)&twx, (size_t)nx_total * sizeof(double2), c->st));
+    k_twiddle<<<(unsigned)((nx_total + 255) / 256), 256, 0, c->st>>>(twx, (int)nx_total);
+    dim3 bl(32, 8), gr((unsigned)((nf + 31) / 32), (unsigned)((nx_total + 7) / 8));
+    k_dft_x<<<gr, bl, 0, c->st>>>(A, pr.rows, (int)nf, c->cfg.x0, (int)nx_total, twx, F);
+    c->launches += 2;
+    CU(cudaGetLastError());
+    int r = split_to_host(c, F, nx_total * nf, out_re, out_im);
+    cudaFreeAsync(A, c->st); cudaFreeAsync(F, c->st); cudaFreeAsync(twx, c->st);
+    return r;
 }
 
 }  // extern "C"

@@ -67,6 +67,15 @@ def source_table(kind, steps, dt, wave_args, start=0):
     return np.array([fn(tt=tt, dt=dt, **wave_args) for tt in range(start, start + steps)], F64)
 
 
+def nonlinspace(spacing):
+    """simulation/analysis.py:9-18: positions from a spacing array (the first spacing is skipped)."""
+    spacing = np.asarray(spacing, F64).reshape(-1)
+    X = np.zeros(spacing.size)
+    for i in range(1, spacing.size):
+        X[i] = X[i - 1] + spacing[i]
+    return X
+
+
 def split_slabs(nx, nparts, min_planes=4):
     """Contiguous x-slabs [x0, x0+n) as evenly as possible."""
     if nparts < 1 or nx < nparts * min_planes:

@@ -50,6 +50,7 @@ cfg = {
     "record_every": 1,
     "chunk_steps": 50,          # steps enqueued per library call (cancel / progress granularity)
     "kernel": "auto",
+    "probes": [],               # [{"u": "uz", "y": j, "z": k}, ...]: (x, t) lines kept on the device for Solver.spectrum()
 }
 
 
@@ -205,6 +206,12 @@ class Solver:
         cm = sec if corner else prim
         e.set_abc(hm.abc_coefficients(cm["c"], cm["p"], dt, fdx, fdy, fdz, sdx, sdy, sdz))
         self.dt, self._x0 = dt, x0
+        self._x, self._fdx, self._nranks = x, fdx, nranks
+        # line probes: the (x, t) matrices analysis.spectrum would re-read from the file stay in HBM
+        self._probes = {}
+        for pr in c.get("probes") or []:
+            key = (pr["u"], int(pr["y"]), int(pr.get("z", 0)))
+            self._probes[key] = e.probe_add(key[0], key[1], key[2], max(1, self.t // int(c["record_every"])))
         self._wave, self._wave_args = c["wave"], dict(c["wave_args"])
 
         self.writer = None
@@ -303,6 +310,32 @@ class Solver:
         from simulation import base_solver     # reference module
         self.init(grid=base_solver.TestDefaults.g, material=base_solver.TestDefaults.m, steps=10)
         self.run()
+
+    def spectrum(self, u_id, z_index, y_index, x_index=None):
+        """simulation/analysis.py:44-96 without the file: (x, f, dft) of the Hann-windowed 1-D (t) or
+        2-D (x, t) transform of u_id[:, y_index, z_index, :], computed on the device from the line
+        probe registered through cfg["probes"].  Multi-GPU: every rank returns the full result."""
+        key = (u_id, int(y_index), int(z_index))
+        if self.engine is None or key not in self._probes:
+            raise KeyError("no probe for %s: add {'u': %r, 'y': %d, 'z': %d} to cfg['probes'] before init()" % ((key,) + key))
+        e, pid = self.engine, self._probes[key]
+        rows, N = e.probe_shape(pid)
+        nxt = self._x.size - (1 if u_id == "ux" else 0)
+        Nf = N // 2
+        x = hm.nonlinspace(self._fdx) if u_id == "ux" else np.array(self._x)
+        f = np.fft.fftfreq(N, d=self.dt * int(self.cfg["record_every"]))[:Nf]
+        window = np.hanning(N)
+        if x_index is None:
+            part = e.probe_dft_xt(pid, window, Nf, nxt)
+            if self._nranks > 1:
+                part = sum(self.allgather(part))
+            return x, f, np.abs(part) / np.sqrt(float(nxt) * N)
+        xi = int(x_index) % nxt
+        mine = self._x0 <= xi < self._x0 + rows
+        line = e.probe_dft_t(pid, window, Nf, xi - self._x0, 1)[0] if mine else None
+        if self._nranks > 1:
+            line = next(a for a in self.allgather(line) if a is not None)
+        return x, f, np.abs(line) / np.sqrt(float(N))
 
     # -- helpers for tests / scripts -----------------------------------------------------------
     def fields(self):

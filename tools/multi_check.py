@@ -14,6 +14,32 @@ from phonomena_b200 import _lib, hostmath as hm
 from phonomena_b200.workloads import crystal_case
 
 
+def spectrum_check(rank, world, local, nx, ny, nz, steps):
+    """Plugin level: Solver.spectrum over slabs (partial 2-D transforms summed over the ranks, the 1-D one
+    taken from the owning rank) against the same call on a single-GPU run of the whole grid."""
+    from phonomena_b200.solver_b200 import Solver
+    g, m = crystal_case(nx, ny, nz).as_grid_material()
+    out = []
+    for slabs in (True, False):
+        s = Solver()
+        s.cfg.update({"wave": "sin", "wave_args": {"f": 100}, "write_mode": "off", "device": local, "slabs_from_env": slabs,
+                      "probes": [{"u": "ux", "y": ny // 3, "z": 0}, {"u": "uz", "y": ny // 2, "z": 2}]})
+        s.init(g, m, steps)
+        s.run()
+        out.append([s.spectrum("ux", 0, ny // 3), s.spectrum("uz", 2, ny // 2), s.spectrum("ux", 0, ny // 3, x_index=nx - 3),
+                    s.spectrum("uz", 2, ny // 2, x_index=1)])
+        s._close_engine()
+    err = 0.0
+    for a, b in zip(*out):
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2].shape == b[2].shape
+        err = max(err, float(np.linalg.norm(a[2] - b[2]) / np.linalg.norm(b[2])))
+    t = torch.tensor([err], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print(json.dumps({"check": "spectrum over slabs vs single GPU", "world": world, "max_rel_l2": float(t[0])}), flush=True)
+    return float(t[0]) <= 1e-12
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -54,6 +80,7 @@ def main():
             print(json.dumps({"halo": mode, "dtype": dtype, "arith": arith, "kernel": kernel, "ranks_identical": int(t[0]), "world": world,
                               "energy": float(t[1])}), flush=True)
         ok = ok and int(t[0]) == world and float(t[1]) > 0
+    ok = spectrum_check(rank, world, local, nx, ny, nz, steps) and ok
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
 
