@@ -85,6 +85,12 @@ int phb_set_spacing(phb_ctx *ctx, const double *fdx, const double *fdy, const do
  * C[3][3], C[4][4], C[5][5] -- and the density (material.py:55-63). */
 int phb_set_material_table(phb_ctx *ctx, int32_t nmat, const double *c12, const double *rho);
 
+/* replaces: Material.C / Material.P handed over as the reference stores them (material.py:48-63;
+ * SURVEY 8a2): C (planes, Ny, Nz, 6, 6) and P (planes, Ny, Nz) float64 for the same planes as
+ * phb_set_material_ids.  The distinct (12 entries read + density) tuples become the material table
+ * and the id map in one call; more distinct cells than the table holds (15) is an error. */
+int phb_set_material_dense(phb_ctx *ctx, const double *C, const double *P, int64_t nplanes);
+
 /* per-cell material id (index into the table), reference layout (planes, Ny, Nz) uint8,
  * for planes x0 .. min(x0+nxl+1, nx)-1  (one extra plane to the right when it exists). */
 int phb_set_material_ids(phb_ctx *ctx, const uint8_t *ids, int64_t nplanes);

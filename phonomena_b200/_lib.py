@@ -22,7 +22,7 @@ REC_UX, REC_UY, REC_UZ = 1, 2, 4
 # every symbol include/phb200.h declares (tests check the .so exports all of them)
 SYMBOLS = (
     "phb_version", "phb_last_error", "phb_device_count", "phb_create", "phb_destroy",
-    "phb_set_spacing", "phb_set_material_table", "phb_set_material_ids", "phb_gen_material_ids",
+    "phb_set_spacing", "phb_set_material_table", "phb_set_material_dense", "phb_set_material_ids", "phb_gen_material_ids",
     "phb_get_material_ids", "phb_set_abc", "phb_set_source_table", "phb_set_fields", "phb_get_fields",
     "phb_get_stress", "phb_run", "phb_sync", "phb_run_timed", "phb_steps_done", "phb_launch_count",
     "phb_info", "phb_profile", "phb_comm_unique_id", "phb_comm_init", "phb_p2p_export", "phb_p2p_import", "phb_record_next", "phb_record_release",
@@ -68,6 +68,7 @@ def load_library(path=None):
     lib.phb_set_spacing.argtypes = [vp] + [dp] * 6
     lib.phb_set_material_table.argtypes = [vp, C.c_int32, dp, dp]
     lib.phb_set_material_ids.argtypes = [vp, u8p, C.c_int64]
+    lib.phb_set_material_dense.argtypes = [vp, dp, dp, C.c_int64]
     lib.phb_gen_material_ids.argtypes = [vp, fp, C.c_int32, dp, dp, dp]
     lib.phb_get_material_ids.argtypes = [vp, u8p]
     lib.phb_set_abc.argtypes = [vp, dp]
@@ -205,6 +206,13 @@ class Engine:
         if ids.shape != (self.id_planes(), self.ny, self.nz):
             raise PhbError("ids has shape %s, expected %s" % (ids.shape, (self.id_planes(), self.ny, self.nz)))
         _chk(self.lib, self.lib.phb_set_material_ids(self._ctx, ids.ctypes.data_as(C.POINTER(C.c_uint8)), ids.shape[0]))
+
+    def set_material_dense(self, Cd, Pd):
+        """The reference's own arrays: C (planes, Ny, Nz, 6, 6), P (planes, Ny, Nz) for planes
+        x0 .. x0 + id_planes() - 1 (Material.C / Material.P, material.py:48-63)."""
+        n = self.id_planes()
+        Cd, Pd = _f64(Cd, (n, self.ny, self.nz, 6, 6)), _f64(Pd, (n, self.ny, self.nz))
+        _chk(self.lib, self.lib.phb_set_material_dense(self._ctx, _dptr(Cd), _dptr(Pd), n))
 
     def gen_material_ids(self, targets, x, y, z):
         """targets: (n,4) float32 rows x, y, z, r -- evaluated on the device."""

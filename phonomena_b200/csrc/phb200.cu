@@ -923,6 +923,43 @@ int phb_set_material_ids(phb_ctx *c, const uint8_t *ids, int64_t nplanes) {
     return 0;
 }
 
+int phb_set_material_dense(phb_ctx *c, const double *C, const double *P, int64_t nplanes) {
+    if (!c) return fail("null context");
+    if (!C || !P) return fail("null argument");
+    int ib, ie;
+    const int np = ids_planes(c, &ib, &ie);
+    if (nplanes != np) return fail("expected %d material planes [%d, %d), got %lld", np, ib, ie, (long long)nplanes);
+    const size_t cells = (size_t)np * c->cfg.ny * c->cfg.nz;
+    // the 12 entries of the 6x6 block the path reads: rows 0..2 x columns 0..2, then (3,3), (4,4), (5,5)
+    static const int pick[12] = {0, 1, 2, 6, 7, 8, 12, 13, 14, 21, 28, 35};
+    std::vector<double> tab;            // nmat x 13 (12 stiffness entries, density)
+    std::vector<uint8_t> ids(cells);
+    int nmat = 0, last = 0;
+    double key[13];
+    for (size_t q = 0; q < cells; ++q) {
+        const double *cq = C + q * 36;
+        for (int a = 0; a < 12; ++a) key[a] = cq[pick[a]];
+        key[12] = P[q];
+        int id = -1;
+        if (nmat && memcmp(key, &tab[(size_t)last * 13], sizeof key) == 0) id = last;
+        for (int m = 0; id < 0 && m < nmat; ++m)
+            if (memcmp(key, &tab[(size_t)m * 13], sizeof key) == 0) id = m;
+        if (id < 0) {
+            if (nmat == MAX_MAT) return fail("more than %d distinct materials in C / P (cell %zu)", (int)MAX_MAT, q);
+            tab.insert(tab.end(), key, key + 13);
+            id = nmat++;
+        }
+        ids[q] = (uint8_t)(last = id);
+    }
+    std::vector<double> c12((size_t)nmat * 12), rho((size_t)nmat);
+    for (int m = 0; m < nmat; ++m) {
+        std::copy(&tab[(size_t)m * 13], &tab[(size_t)m * 13] + 12, &c12[(size_t)m * 12]);
+        rho[(size_t)m] = tab[(size_t)m * 13 + 12];
+    }
+    if (int r = phb_set_material_table(c, nmat, c12.data(), rho.data())) return r;
+    return phb_set_material_ids(c, ids.data(), nplanes);
+}
+
 int phb_gen_material_ids(phb_ctx *c, const float *tg, int32_t n, const double *x, const double *y, const double *z) {
     ENTER(c);
     if (n < 0 || (n && !tg) || !x || !y || !z) return fail("bad arguments");

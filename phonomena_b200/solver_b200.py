@@ -50,6 +50,8 @@ cfg = {
     "record_every": 1,
     "chunk_steps": 50,          # steps enqueued per library call (cancel / progress granularity)
     "kernel": "auto",
+    "material": "inclusions",   # "inclusions": primary/secondary + inclusion list, filled on the device (what Material.update
+                                # builds) | "arrays": take material.C / material.P as they are (any <= 15 distinct cells)
     "probes": [],               # [{"u": "uz", "y": j, "z": k}, ...]: (x, t) lines kept on the device for Solver.spectrum()
 }
 
@@ -197,13 +199,25 @@ class Solver:
             # default torch.distributed), NCCL send/recv as fallback
             self.halo = e.connect(rank, nranks, self.allgather, self.broadcast, mode=c.get("halo"))
         e.set_spacing(fdx, fdy, fdz, sdx, sdy, sdz)
-        e.set_material_table([prim["c"], sec["c"]], [prim["p"], sec["p"]])
-        e.gen_material_ids(targets, mx, my, mz)
-        ids = e.get_material_ids() if (rec_mode != "off" or x0 == 0) else None
-        corner = int(ids[0, 0, 0]) if (ids is not None and x0 == 0) else 0
-        if nranks > 1:      # the Mur coefficients come from the corner cell (0,0,0), which rank 0 owns
-            corner = int(self.broadcast(corner if rank == 0 else None))
-        cm = sec if corner else prim
+        dense = c.get("material", "inclusions") == "arrays"
+        if dense:
+            # the reference's own per-cell arrays (material.py:48-63): whatever the caller put there
+            Cd, Pd = np.asarray(material.C), np.asarray(material.P)
+            if Pd.shape != (x.size, y.size, z.size) or Cd.shape != Pd.shape + (6, 6):
+                raise ValueError("material.C / material.P have shapes %s / %s for a %s grid" % (Cd.shape, Pd.shape, (x.size, y.size, z.size)))
+            sl = slice(x0, x0 + e.id_planes())
+            e.set_material_dense(Cd[sl], Pd[sl])
+            cm = {"c": np.array(Cd[0, 0, 0], np.float64), "p": float(Pd[0, 0, 0])}
+            P_out = np.array(Pd[x0:x0 + nxl], np.float64) if rec_mode != "off" else None
+            C_out = Cd[x0:x0 + nxl]
+        else:
+            e.set_material_table([prim["c"], sec["c"]], [prim["p"], sec["p"]])
+            e.gen_material_ids(targets, mx, my, mz)
+            ids = e.get_material_ids() if (rec_mode != "off" or x0 == 0) else None
+            corner = int(ids[0, 0, 0]) if (ids is not None and x0 == 0) else 0
+            if nranks > 1:      # the Mur coefficients come from the corner cell (0,0,0), which rank 0 owns
+                corner = int(self.broadcast(corner if rank == 0 else None))
+            cm = sec if corner else prim
         e.set_abc(hm.abc_coefficients(cm["c"], cm["p"], dt, fdx, fdy, fdz, sdx, sdy, sdz))
         self.dt, self._x0 = dt, x0
         self._x, self._fdx, self._nranks = x, fdx, nranks
@@ -217,7 +231,7 @@ class Solver:
         self.writer = None
         if rec_mode != "off":
             frames = self.t // int(c["record_every"])
-            P = np.where(ids == 1, sec["p"], prim["p"]).astype(np.float64)
+            P = P_out if dense else np.where(ids == 1, sec["p"], prim["p"]).astype(np.float64)
             attrs = {"x": x, "y": y, "z": z,
                      "sdx": sdx.reshape(-1, 1, 1), "sdy": sdy.reshape(1, -1, 1), "sdz": sdz.reshape(1, 1, -1),
                      "fdx": fdx.reshape(-1, 1, 1), "fdy": fdy.reshape(1, -1, 1), "fdz": fdz.reshape(1, 1, -1),
@@ -225,7 +239,7 @@ class Solver:
                      "solver_cfg": json.dumps(c), "x0": int(x0), "nxl": int(nxl)}
             meta = {"attrs": attrs, "density": P, "elasticity": None}
             if rec_mode == "full" and P.size <= 1 << 22:      # the reference's `elasticity` is 288 B/cell
-                meta["elasticity"] = np.where((ids == 1)[..., None, None], sec["c"], prim["c"])
+                meta["elasticity"] = np.array(C_out, np.float64) if dense else np.where((ids == 1)[..., None, None], sec["c"], prim["c"])
             path = self.file if nranks == 1 else "%s.rank%d" % (self.file, rank)      # one file per slab
             self.writer = Writer(path, e, meta, frames, rec_mode, int(c["record_every"]))
             self.writer.start()

@@ -116,3 +116,67 @@ def test_plugin_does_not_mutate_caller_objects(tmp_path):
     g.x[:] = -1            # the caller may free / reuse its arrays after init()
     s.run()
     assert np.array_equal(x0, d["x"]) and s.stats["steps"] == 3
+
+
+def _arrays_material(d, C, P):
+    g, m = fake_from_golden(d)
+    m.C, m.P = C, P
+    return g, m
+
+
+def test_plugin_material_from_reference_arrays(tmp_path):
+    """cfg material='arrays': Material.C / Material.P as the reference stores them."""
+    from oracle import fdtd_numpy as onp
+    d = H.load_golden("default_json_1000")
+    C, P = onp.set_constants(d["x"], d["y"], d["z"], H.targets_of(d), d["prim_c"], d["prim_p"], d["sec_c"], d["sec_p"])
+    s = make_solver(d, tmp_path, record="full", material="arrays")
+    g, m = _arrays_material(d, C, P)
+    g.targets = g.targets[:0]                  # the inclusion list must not be what is used
+    s.init(g, m, 200)
+    s.run()
+    from phonomena_b200.h5lite import H5Reader
+    r = H5Reader(s.file)
+    assert np.array_equal(r.read("density"), P) and np.array_equal(r.read("elasticity"), C)
+    assert np.array_equal(r.read("uz", frame=99)[:, :, 0], d["snap_uz_100"])
+    assert np.array_equal(r.read("ux", frame=9)[:, :, 0], d["snap_ux_10"])
+
+
+@pytest.mark.parametrize("precision,arith,tol", [("fp64", "exact", 0.0), ("fp64", "fast", 1e-12), ("fp32", "fast", 1e-5)])
+def test_plugin_three_material_medium_matches_oracle(tmp_path, precision, arith, tol):
+    """More than the reference's two materials, straight from C / P: a third (and fourth) material in
+    blocks that cut through inclusions, the corner cell and the boundary planes."""
+    d = H.load_golden("crystal_48x32x12")
+    o = H.oracle_from_golden(d)
+    C, P = o.C.copy(), o.P.copy()
+    third = d["sec_c"] * 0.37
+    third[0, 2] *= 1.11                        # keep it non-symmetric like the shipped tables (App. B #4)
+    C[5:19, 3:17, :7], P[5:19, 3:17, :7] = third, 2700.0
+    C[0:3, 0:4, 0:2], P[0:3, 0:4, 0:2] = d["prim_c"] * 1.5, 4000.0      # the Mur corner cell
+    C[-2:, :, -3:], P[-2:, :, -3:] = third, 2700.0
+    from oracle import fdtd_numpy as onp
+    o2 = onp.OracleSolver(d["x"], d["y"], d["z"], C, P, o.dt, wave=d["wave"], wave_args=d["wave_args"])
+    o2.run(60)
+    s = make_solver(d, tmp_path, record="off", write_mode="off", material="arrays", precision=precision, arith=arith)
+    g, m = _arrays_material(d, C, P)
+    s.init(g, m, 60)
+    assert s.dt == o.dt
+    s.run()
+    got, ref = s.fields(), (o2.ux, o2.uy, o2.uz)
+    if tol == 0.0:
+        assert all(np.array_equal(a, b) for a, b in zip(got, ref))
+    else:
+        assert H.rel_l2(got, ref) <= tol
+
+
+def test_plugin_material_arrays_errors(tmp_path):
+    d = H.load_golden("testdefaults")
+    o = H.oracle_from_golden(d)
+    s = make_solver(d, tmp_path, record="off", write_mode="off", material="arrays")
+    g, m = _arrays_material(d, o.C[:-1], o.P[:-1])
+    with pytest.raises(ValueError, match="shapes"):
+        s.init(g, m, 2)
+    C, P = o.C.copy(), o.P.copy()
+    P.reshape(-1)[:40] += np.arange(40)        # 40 distinct densities
+    g, m = _arrays_material(d, C, P)
+    with pytest.raises(Exception, match="distinct materials"):
+        s.init(g, m, 2)
