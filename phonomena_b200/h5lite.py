@@ -15,6 +15,7 @@ validated by the independent reader below and by structure tests, not by libhdf5
 """
 from __future__ import annotations
 
+import mmap
 import struct
 
 import numpy as np
@@ -229,7 +230,9 @@ class H5Reader:
     """Parses exactly what H5Writer emits, following the addresses stored in the file."""
 
     def __init__(self, path):
-        self.b = open(path, "rb").read()
+        self._fh = open(path, "rb")
+        self.b = mmap.mmap(self._fh.fileno(), 0, access=mmap.ACCESS_READ)     # frames are read where they lie
+        self._chunks = {}
         b = self.b
         if b[:8] != SIG:
             raise ValueError("not an HDF5 file")
@@ -256,7 +259,7 @@ class H5Reader:
             nsym = struct.unpack_from("<H", b, snod + 6)[0]
             for s in range(nsym):
                 noff, oaddr = struct.unpack_from("<QQ", b, snod + 8 + s * 40)
-                end = b.index(b"\0", heap_data + noff)
+                end = b.find(b"\0", heap_data + noff)
                 self.datasets[b[heap_data + noff:end].decode()] = oaddr
 
     def _messages(self, addr):
@@ -316,8 +319,10 @@ class H5Reader:
         bt = struct.unpack_from("<Q", layout, 3)[0]
         cdims = struct.unpack_from("<%dI" % nd, layout, 11)
         assert tuple(cdims[:-1]) == tuple(shape[:-1]) + (1,) and cdims[-1] == 8
-        chunks = {}
-        self._walk(bt, nd, chunks)
+        if name not in self._chunks:
+            self._chunks[name] = {}
+            self._walk(bt, nd, self._chunks[name])
+        chunks = self._chunks[name]
         fshape = tuple(shape[:-1])
         n = int(np.prod(fshape))
         if frame is not None:
@@ -343,3 +348,32 @@ class H5Reader:
             else:
                 self._walk(child, nd, out)
             pos += keysize + 8
+
+
+def merge_slabs(paths, out_path):
+    """Concatenate the per-slab output files of a multi-GPU run (attrs x0 / nxl, one file per rank,
+    solver_b200.Solver) along x into one file with the single-GPU schema.  Frame by frame, so the
+    working set is one frame."""
+    rs = sorted((H5Reader(p) for p in paths), key=lambda r: int(r.attrs["x0"]))
+    x0 = 0
+    for r in rs:
+        if int(r.attrs["x0"]) != x0:
+            raise ValueError("slab files do not tile x: expected a slab starting at %d, found %d" % (x0, int(r.attrs["x0"])))
+        x0 += int(r.attrs["nxl"])
+    nx = len(np.atleast_1d(rs[0].attrs["x"]))
+    if x0 != nx:
+        raise ValueError("slab files cover %d of %d planes" % (x0, nx))
+    frames = min(int(r.attrs.get("frames_written", r.shape("uz")[3])) for r in rs)
+    with H5Writer(out_path) as w:
+        w.attrs.update(rs[0].attrs)
+        w.attrs.update({"x0": 0, "nxl": nx, "frames_written": frames})
+        for name in ("density", "elasticity"):
+            if all(name in r.datasets for r in rs):
+                w.create_dataset(name, np.concatenate([r.read(name) for r in rs], axis=0))
+        for name in ("ux", "uy", "uz"):
+            shapes = [r.shape(name) for r in rs]
+            full = (sum(sh[0] for sh in shapes),) + tuple(shapes[0][1:3]) + (shapes[0][3],)
+            d = w.create_chunked(name, full)
+            for t in range(frames):
+                w.write_frame(d, t, np.concatenate([r.read(name, frame=t) for r in rs], axis=0))
+    return out_path

@@ -35,7 +35,7 @@ import time
 import numpy as np
 
 from . import _lib, hostmath as hm
-from .h5lite import H5Writer
+from .h5lite import H5Writer, merge_slabs
 
 logger = logging.getLogger(__name__)
 
@@ -52,6 +52,7 @@ cfg = {
     "kernel": "auto",
     "material": "inclusions",   # "inclusions": primary/secondary + inclusion list, filled on the device (what Material.update
                                 # builds) | "arrays": take material.C / material.P as they are (any <= 15 distinct cells)
+    "merge_slabs": True,        # multi-GPU: concatenate the per-slab files into `file` after the run (rank 0)
     "probes": [],               # [{"u": "uz", "y": j, "z": k}, ...]: (x, t) lines kept on the device for Solver.spectrum()
 }
 
@@ -288,6 +289,14 @@ class Solver:
             self.running.clear()
             if self.writer is not None:
                 self.writer.finish()
+        if self._nranks > 1 and self.writer is not None and c.get("merge_slabs", True):
+            # every slab file is closed (the all-gather doubles as the barrier); rank 0 concatenates along x
+            parts = self.allgather(self.writer.path)
+            if self._x0 == 0:
+                merge_slabs(parts, self.file)
+                for p in parts:
+                    os.remove(p)
+            self.allgather(None)
         etime = time.time() - stime
         cells = e.nx * e.ny * e.nz
         self.stats = {"steps": done, "seconds": etime, "gcells_per_s": cells * done / etime / 1e9 if etime > 0 else 0.0,

@@ -130,3 +130,36 @@ def test_bench_reference_arm_contract_line():
     assert line["impl"] == "reference" and line["metric"] == "Gcell-updates/s" and line["unit"] == "Gcell/s"
     assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"] and "workload" in line["config"]
+
+
+def test_merge_slabs_reassembles_single_gpu_schema(tmp_path):
+    """h5lite.merge_slabs: per-slab files (attrs x0 / nxl, the plugin's multi-GPU output) -> one file."""
+    from phonomena_b200.h5lite import H5Reader, H5Writer, merge_slabs
+    rng = np.random.default_rng(5)
+    nx, ny, N = 11, 4, 70
+    full = {"ux": rng.standard_normal((nx - 1, ny, 1, N)), "uy": rng.standard_normal((nx, ny - 1, 1, N)),
+            "uz": rng.standard_normal((nx, ny, 1, N))}
+    dens = rng.uniform(1, 2, (nx, ny, 3))
+    parts = []
+    for r, (x0, nxl) in enumerate(((0, 4), (4, 4), (8, 3))):
+        p = str(tmp_path / ("o.h5.rank%d" % r))
+        with H5Writer(p) as w:
+            w.attrs.update({"x": np.arange(nx, dtype=float), "dt": 1e-5, "steps": N, "x0": x0, "nxl": nxl,
+                            "frames_written": N if r else N - 2, "prim_material": "GaAs"})
+            w.create_dataset("density", dens[x0:x0 + nxl])
+            for name, a in full.items():
+                rows = min(x0 + nxl, a.shape[0]) - x0
+                d = w.create_chunked(name, (rows,) + a.shape[1:])
+                for t in range(N if r else N - 2):
+                    w.write_frame(d, t, a[x0:x0 + rows, ..., t])
+        parts.append(p)
+    out = merge_slabs(parts[::-1], str(tmp_path / "o.h5"))
+    r = H5Reader(out)
+    assert r.attrs["x0"] == 0 and r.attrs["nxl"] == nx and r.attrs["frames_written"] == N - 2 and r.attrs["prim_material"] == "GaAs"
+    assert np.array_equal(r.read("density"), dens)
+    for name, a in full.items():
+        assert r.shape(name) == a.shape
+        for t in (0, 33, N - 3):
+            assert np.array_equal(r.read(name, frame=t), a[..., t])
+    with pytest.raises(ValueError, match="tile"):
+        merge_slabs(parts[1:], str(tmp_path / "bad.h5"))

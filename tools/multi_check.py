@@ -19,25 +19,39 @@ def spectrum_check(rank, world, local, nx, ny, nz, steps):
     taken from the owning rank) against the same call on a single-GPU run of the whole grid."""
     from phonomena_b200.solver_b200 import Solver
     g, m = crystal_case(nx, ny, nz).as_grid_material()
-    out = []
+    out, files = [], []
     for slabs in (True, False):
         s = Solver()
-        s.cfg.update({"wave": "sin", "wave_args": {"f": 100}, "write_mode": "off", "device": local, "slabs_from_env": slabs,
+        s.cfg.update({"wave": "sin", "wave_args": {"f": 100}, "write_mode": "thread", "record": "surface", "arith": "exact",
+                      "device": local, "slabs_from_env": slabs, "record_every": 4,
                       "probes": [{"u": "ux", "y": ny // 3, "z": 0}, {"u": "uz", "y": ny // 2, "z": 2}]})
         s.init(g, m, steps)
         s.run()
-        out.append([s.spectrum("ux", 0, ny // 3), s.spectrum("uz", 2, ny // 2), s.spectrum("ux", 0, ny // 3, x_index=nx - 3),
-                    s.spectrum("uz", 2, ny // 2, x_index=1)])
+        out.append([s.spectrum("ux", 0, ny // 3), s.spectrum("uz", 2, ny // 2), s.spectrum("ux", 0, ny // 3, x_index=1),
+                    s.spectrum("uz", 2, ny // 2, x_index=-world)])
         s._close_engine()
+        files.append(s.file)
+    same_file = 1.0
+    if rank == 0:      # the merged slab file against the single-GPU file: same schema, same frames
+        from phonomena_b200.h5lite import H5Reader
+        a, b = H5Reader(files[0]), H5Reader(files[1])
+        same_file = float(all(a.shape(k) == b.shape(k) and np.array_equal(a.read(k), b.read(k)) for k in ("ux", "uy", "uz", "density"))
+                          and a.attrs["frames_written"] == b.attrs["frames_written"] == steps // 4 and a.attrs["nxl"] == nx
+                          and not os.path.exists(files[0] + ".rank0"))
+    for f in files:
+        if os.path.exists(f):
+            os.remove(f)
     err = 0.0
     for a, b in zip(*out):
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2].shape == b[2].shape
+        assert np.linalg.norm(b[2]) > 0          # probes sit where the wave already is
         err = max(err, float(np.linalg.norm(a[2] - b[2]) / np.linalg.norm(b[2])))
-    t = torch.tensor([err], dtype=torch.float64, device="cuda")
+    t = torch.tensor([err, 1.0 - same_file], dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
-        print(json.dumps({"check": "spectrum over slabs vs single GPU", "world": world, "max_rel_l2": float(t[0])}), flush=True)
-    return float(t[0]) <= 1e-12
+        print(json.dumps({"check": "plugin over slabs vs single GPU", "world": world, "spectrum_max_rel_l2": float(t[0]),
+                          "merged_file_identical": int(t[1] == 0)}), flush=True)
+    return float(t[0]) <= 1e-12 and float(t[1]) == 0
 
 
 def main():
@@ -80,7 +94,7 @@ def main():
             print(json.dumps({"halo": mode, "dtype": dtype, "arith": arith, "kernel": kernel, "ranks_identical": int(t[0]), "world": world,
                               "energy": float(t[1])}), flush=True)
         ok = ok and int(t[0]) == world and float(t[1]) > 0
-    ok = spectrum_check(rank, world, local, nx, ny, nz, steps) and ok
+    ok = spectrum_check(rank, world, local, nx, ny, nz, int(os.environ.get("PHB_MC_LONG", "1000"))) and ok      # the wave crosses every slab
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
 
