@@ -115,6 +115,24 @@ def cpu_sample(threads, steps, warmup, n=128):
     return n ** 3 * steps / dt / 1e9, "%d^3 block of the same crystal, %d steps, NumPy float64, %d thread(s)" % (n, steps, threads)
 
 
+def cpu_sample_c(steps, warmup, n=256):
+    """Context only: the C restatement (oracle/fdtd_c.c, bit-identical to the NumPy one) with OpenMP on every
+    host core -- a far stronger CPU program than the reference's NumPy, reported beside it, never as the baseline."""
+    from oracle import fdtd_c, fdtd_numpy as onp
+    from phonomena_b200.workloads import crystal_case
+    c = crystal_case(n, n, n)
+    ids = onp.material_id_map(c.x, c.y, c.z, onp.make_targets(c.targets.tolist()))
+    o = fdtd_c.COracle(c.x, c.y, c.z, ids, [c.prim_c, c.sec_c], [c.prim_p, c.sec_p], c.dt, wave="sin", wave_args={"f": 100}, omp=True)
+    o.run(warmup)
+    t0 = time.perf_counter()
+    o.run(steps)
+    dt = time.perf_counter() - t0
+    o.close()
+    cores = int(os.environ.get("OMP_NUM_THREADS", 0)) or len(os.sched_getaffinity(0))
+    return {"value": n ** 3 * steps / dt / 1e9, "unit": UNIT, "cores": cores,
+            "sample": "%d^3 block of the same crystal, %d steps, C + OpenMP (gcc -O2 -ffp-contract=off), float64" % (n, steps)}
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path = NumPy slicing
     arithmetic, timed through the oracle port (the reference is pure Python and does not travel to
@@ -135,6 +153,10 @@ def run_reference(args):
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "host": {"cpu_count": os.cpu_count(), "affinity": len(os.sched_getaffinity(0)), "numpy": np.__version__},
     }
+    try:
+        line["extra"] = {"c_openmp_port": cpu_sample_c(steps, 1)}
+    except Exception as exc:      # context only
+        line["extra"] = {"c_openmp_port": {"error": str(exc)[:200]}}
     print(json.dumps(line), flush=True)
 
 
