@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libphb200.so")
+# PHB200_LIB: development override (timing variants built by tools/diag_build.sh); still a CUDA library, not a fallback
+LIB_PATH = os.environ.get("PHB200_LIB") or os.path.join(_HERE, "libphb200.so")
 
 F32, F64 = 0, 1
 FAST, EXACT, COMP = 0, 1, 2

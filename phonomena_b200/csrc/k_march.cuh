@@ -45,6 +45,17 @@
 #ifndef PHB_UNROLL
 #define PHB_UNROLL 2
 #endif
+#ifndef PHB_NSO_RW2
+#define PHB_NSO_RW2 3
+#endif
+// Development-only timing variants (never built into libphb200.so; tools/diag_build.sh):
+//   PHB_DIAG == 1  "memory only": the TMA ring, the u_old ring and the vector stores run, the arithmetic and the
+//                  warp-to-warp exchange do not -> the rate the load/store pipeline allows
+//   PHB_DIAG == 2  "compute only": nothing is loaded (the tiles hold whatever shared memory holds), arithmetic,
+//                  exchange and stores run -> the rate the per-warp dependency chains allow
+#ifndef PHB_DIAG
+#define PHB_DIAG 0
+#endif
 
 namespace phb {
 
@@ -52,11 +63,16 @@ template <class T> struct VecOf;
 template <> struct VecOf<float> { static constexpr int V = 4; };
 template <> struct VecOf<double> { static constexpr int V = 2; };
 
-template <class T, int R, int NST>
+// R = tile rows (TY = R - 2 of them produce output), RW = rows per warp (R / RW warps), NST = depth of the u_cur ring.
+template <class T, int R, int NST, int RW = 1>
 struct MarchCfg {
+    static_assert(R % RW == 0, "rows per warp must divide the tile rows");
     static constexpr int V = VecOf<T>::V;
     static constexpr int SZ = (int)sizeof(T);
-    static constexpr int NSO = (NST >= 4) ? 2 : NST;   // depth of the u_old ring (4+2 or 3+3 stages fit 227 KB)
+    static constexpr int W = R / RW;                  // warps per block
+    // depth of the u_old ring: 4 + 2 stages fit 227 KB with one row per warp; two rows per warp halve the
+    // exchange tiles, which pays for a third u_old stage
+    static constexpr int NSO = (NST >= 4) ? (RW >= 2 ? PHB_NSO_RW2 : 2) : NST;
     static constexpr int TZ = 32 * V;                 // cells per tile row
     static constexpr int TY = R - 2;                  // output rows per tile
     static constexpr int ROWB = 34 * 16;              // u_cur ring row: 34 vectors of 16 B (halo vector each side)
@@ -70,17 +86,18 @@ struct MarchCfg {
     static constexpr int OSTAGE = 3 * OCOMP;          // u_old stage layout: [O x3]
     static constexpr int OFF_O = NST * STAGE;
     static constexpr int XROWB = 32 * 16;
-    static constexpr int XCOMP = R * XROWB;
-    static constexpr int XBUF = 3 * XCOMP;            // T2, T4, T6
+    static constexpr int XCOMP = W * XROWB;           // one vector per lane and warp
+    static constexpr int XBUF = 3 * XCOMP;            // T2 (first row of the warp), T4, T6 (its last row)
     static constexpr int OFF_X = OFF_O + NSO * OSTAGE;
     static constexpr int OFF_BAR = OFF_X + 2 * XBUF;
-    static constexpr int NBAR = 2 * NST + NSO + 2 * R;   // full[NST], done[NST], fullO[NSO], pub[R][2]
+    static constexpr int NBAR = 2 * NST + NSO + 2 * W;   // full[NST], done[NST], fullO[NSO], pub[W][2]
     static constexpr int OFF_SX = OFF_BAR + (NBAR * 8 + 8 + 127) / 128 * 128;   // + the `issued` counter
     static constexpr uint32_t TX_U = 3u * UCOMP + CTILE;   // bytes per u_cur stage / u_old stage
     static constexpr uint32_t TX_O = 3u * OCOMP;
-    // x-spacing table: 2 values per plane for planes [ia-2, ib+1]; z table [2][TZ]; y table [R][2]; class table
+    // x-spacing table: 2 values per plane for planes [ia-2, ib+1]; z table [2][TZ]; y table [R][2]; the two z
+    // spacings of the tile's halo columns; class table
     __host__ __device__ static size_t off_ztab(int chunk) { return (size_t)OFF_SX + ((size_t)2 * (chunk + 4) * SZ + 127) / 128 * 128; }
-    __host__ __device__ static size_t off_tab(int chunk) { return off_ztab(chunk) + ((size_t)(2 * TZ + 2 * R) * SZ + 127) / 128 * 128; }
+    __host__ __device__ static size_t off_tab(int chunk) { return off_ztab(chunk) + ((size_t)(2 * TZ + 2 * R + 2) * SZ + 127) / 128 * 128; }
     __host__ __device__ static size_t smem_bytes(int chunk, int ncls) { return off_tab(chunk) + (size_t)ncls * CLS_W * SZ; }
 };
 
@@ -204,15 +221,16 @@ struct MarchMaps {
 };
 
 // ---- the kernel ---------------------------------------------------------------------------------
-template <class A, int R, int NST, bool PUSH>
-__global__ void __launch_bounds__(R * 32, (R <= 8 ? 2 : 1))
+template <class A, int R, int NST, bool PUSH, int RW>
+__global__ void __launch_bounds__(R / RW * 32, ((R <= 8 && RW == 1) ? 2 : 1))
 k_step_march(const __grid_constant__ MarchMaps tm, StepArgs<typename A::T> p, MatCls<typename A::T> m, int chunk) {
     using T = typename A::T;
-    using C_ = MarchCfg<T, R, NST>;
-    constexpr int V = C_::V, SZ = C_::SZ, TZ = C_::TZ;
+    using C_ = MarchCfg<T, R, NST, RW>;
+    constexpr int V = C_::V, SZ = C_::SZ, TZ = C_::TZ, W = C_::W, NT = W * 32;
     constexpr int UCE = C_::UCOMP / SZ, OCE = C_::OCOMP / SZ, XCE = C_::XCOMP / SZ;   // component strides in elements
     static_assert(NST >= C_::NSO, "u_cur ring must be at least as deep as the u_old ring");
     constexpr int ROWE = C_::ROWB / SZ;
+    constexpr uint32_t kClsMask = (PHB_DIAG == 2) ? 3u : 255u;   // compute-only timing variant: tiles are never loaded
     using PV = Pack<T, V>;
     using CW = typename std::conditional<V == 4, uint32_t, uint16_t>::type;            // V class bytes
     const Geo<T> &g = p.g;
@@ -220,14 +238,15 @@ k_step_march(const __grid_constant__ MarchMaps tm, StepArgs<typename A::T> p, Ma
     extern __shared__ __align__(1024) unsigned char sm[];
     const uint32_t sb = smem_u32(sm);
 
-    const int lane = threadIdx.x & 31, r = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int r0 = w * RW;                           // first tile row of this warp (rows r0 .. r0 + RW - 1)
     const int k0t = blockIdx.x * TZ;                 // first cell of the tile row
     const int j0 = blockIdx.y * C_::TY;              // first output row
     // planes [ia, ib): x-chunk blockIdx.z of [i_begin, i_end), or (edge launch) the single planes i_begin / edge_b
     const int ia = (p.edge_b >= 0) ? (blockIdx.z == 0 ? p.i_begin : p.edge_b) : p.i_begin + blockIdx.z * chunk;
     const int ib = (p.edge_b >= 0) ? ia + 1 : min(ia + chunk, p.i_end);
     if (ia >= ib) return;
-    const int j = j0 - 1 + r;
+    const int j = j0 - 1 + r0;                       // y index of the warp's first row
     const int kb = k0t + lane * V;                   // first cell of this lane
     const bool k0c = (kb == 0);                      // element 0 of this thread is the k = 0 plane
     const int nplanes = (ib - ia) + 2;               // planes ia-1 .. ib, consumed in order q = 0, 1, ...
@@ -240,19 +259,19 @@ k_step_march(const __grid_constant__ MarchMaps tm, StepArgs<typename A::T> p, Ma
     // small tables: x spacings per plane, z spacings per cell of the tile row, y spacings per row
     T *const sxp = reinterpret_cast<T *>(sm + C_::OFF_SX);                        // [plane-(ia-2)][2] = fdx, sdx
     T *const ztab = reinterpret_cast<T *>(sm + C_::off_ztab(chunk));              // [2][TZ] = fdz[k], sdz[k-1]
-    T *const ytab = ztab + 2 * TZ;                                                // [R][2]  = fdy[j], sdy[j-1]
+    T *const ytab = ztab + 2 * TZ;                                                // [R][2]  = fdy[j], sdy[j-1]; then fdz[kL], sdz[kR-1]
     const T *const stab = reinterpret_cast<const T *>(__builtin_assume_aligned(sm + C_::off_tab(chunk), 128));
 
     // ---- one-time setup ----
     {
         T *tabw = reinterpret_cast<T *>(sm + C_::off_tab(chunk));
-        for (int q = threadIdx.x; q < m.ncls * CLS_W; q += R * 32) tabw[q] = m.tab[q];
-        for (int q = threadIdx.x; q < nplanes + 2; q += R * 32) {
+        for (int q = threadIdx.x; q < m.ncls * CLS_W; q += NT) tabw[q] = m.tab[q];
+        for (int q = threadIdx.x; q < nplanes + 2; q += NT) {
             const int n = min(max(ia - 2 + q, -1), g.nx);          // tables are addressable on [-1, n]
             sxp[2 * q + 0] = g.fdx[n];
             sxp[2 * q + 1] = g.sdx[n];
         }
-        for (int q = threadIdx.x; q < TZ; q += R * 32) {
+        for (int q = threadIdx.x; q < TZ; q += NT) {
             const int k = min(k0t + q, g.nz);
             ztab[q] = g.fdz[k];
             ztab[TZ + q] = (k == 0) ? g.sdz0 : g.sdz[k - 1];       // k = 0 uses sdz[0] (App. B #1)
@@ -262,10 +281,14 @@ k_step_march(const __grid_constant__ MarchMaps tm, StepArgs<typename A::T> p, Ma
             ytab[2 * threadIdx.x + 0] = g.fdy[jj];
             ytab[2 * threadIdx.x + 1] = g.sdy[jj - 1];
         }
+        if (threadIdx.x == R) {   // halo columns kL = k0t - 1 (shear) and kR = k0t + TZ (its T3 needs sdz[kR - 1])
+            ytab[2 * R + 0] = g.fdz[k0t - 1];
+            ytab[2 * R + 1] = g.sdz[min(k0t + TZ - 1, g.nz)];
+        }
         if (threadIdx.x == 0) {
-            for (int s = 0; s < NST; ++s) { mbar_init(bar_full + s * 8, 1); mbar_init(bar_empty + s * 8, R); }
+            for (int s = 0; s < NST; ++s) { mbar_init(bar_full + s * 8, 1); mbar_init(bar_empty + s * 8, W); }
             for (int s = 0; s < NSO; ++s) mbar_init(bar_fullO + s * 8, 1);
-            for (int q = 0; q < 2 * R; ++q) mbar_init(bar_pub + q * 8, (q / 2 == 0 || q / 2 == R - 1) ? 1 : 2);   // arrivals = neighbours
+            for (int q = 0; q < 2 * W; ++q) mbar_init(bar_pub + q * 8, (q / 2 == 0 || q / 2 == W - 1) ? 1 : 2);   // arrivals = neighbours
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
     }
@@ -298,44 +321,58 @@ k_step_march(const __grid_constant__ MarchMaps tm, StepArgs<typename A::T> p, Ma
     // `issued` = next claim.  Nobody blocks to produce: the lane that sees a `done[s]` phase complete
     // after its own arrival claims with a CAS and issues.
     if (threadIdx.x == 0) {
-        for (int c = 0; c < NST; ++c) issue(c);
-        *issued = NST;
+        if (PHB_DIAG != 2) for (int c = 0; c < NST; ++c) issue(c);
+        *issued = (PHB_DIAG == 2) ? nclaims : NST;
     }
     __syncthreads();
 
     // ---- loop-invariant per-thread quantities (kept few: everything else is re-read from smem) ----
-    const bool in_box = (j >= 0 && j < g.ny && kb < g.nzp);      // global vector stores allowed
-    const bool row_out = (r >= 1 && r <= R - 2) && (j < g.ny);    // this WARP produces u_new (warp-uniform)
-    // halo-row warps only produce what their one neighbour reads: the bottom row (r = 0) T4 and T6,
-    // the top row (r = R-1) T2; everything else they would compute is dead (warp-uniform branches)
-    const bool need_shear = (r != R - 1), need_normal = (r != 0);
-    const bool haveL = (lane == 0) && (k0t >= 1) && (j >= 0 && j < g.ny) && row_out;   // halo column kL = k0t-1
-    const bool haveR = (lane == 31) && (k0t + TZ <= g.nz - 1) && (j >= 0 && j < g.ny) && row_out;   // halo column kR
-    const int eo = r * ROWE + (lane + 1) * V;          // own vector inside a u_cur component tile (elements)
-    const int eS = (r >= 1) ? -ROWE : 0, eN = (r <= R - 2) ? ROWE : 0;            // neighbour rows (clamped)
-    const int xo = r * (TZ) + lane * V;                // own vector inside an exchange component tile
-    const int xS = (r >= 1) ? -TZ : 0, xN = (r <= R - 2) ? TZ : 0;
-    const uint32_t pubO = bar_pub + (uint32_t)r * 16;
+    // Row q of the warp is tile row r0 + q, y index j + q.  The first and last TILE rows are the y-halo rows:
+    // they only produce what their one neighbour reads (bottom row: T4 and T6, top row: T2); everything else
+    // they would compute is dead (warp-uniform branches).
+    bool row_out[RW], in_box[RW], need_shear[RW], need_normal[RW];
+    bool any_out = false;
+#pragma unroll
+    for (int q = 0; q < RW; ++q) {
+        const int rr = r0 + q;
+        row_out[q] = (rr >= 1 && rr <= R - 2) && (j + q < g.ny);           // this row produces u_new (warp-uniform)
+        in_box[q] = (j + q >= 0 && j + q < g.ny && kb < g.nzp);            // global vector stores allowed
+        need_shear[q] = (rr != R - 1);
+        need_normal[q] = (rr != 0);
+        any_out = any_out || row_out[q];
+    }
+    const bool haveL = (lane == 0) && (k0t >= 1);                  // halo column kL = k0t-1 exists
+    const bool haveR = (lane == 31) && (k0t + TZ <= g.nz - 1);     // halo column kR = k0t+TZ exists
+    const int eo = r0 * ROWE + (lane + 1) * V;         // own vector (row 0 of the warp) inside a u_cur component tile (elements)
+    const int eS = (r0 >= 1) ? -ROWE : 0;              // row below the warp's first row (clamped)
+    const int eN = (r0 + RW - 1 <= R - 2) ? ROWE : 0;  // row above the warp's last row (clamped), relative to that row
+    const int xo = w * TZ + lane * V;                  // own vector inside an exchange component tile
+    const int xS = (w >= 1) ? -TZ : 0, xN = (w <= W - 2) ? TZ : 0;
+    const uint32_t pubO = bar_pub + (uint32_t)w * 16;
     const T *const zt = ztab + lane * V;               // this lane's z spacings
-    const T *const yt = ytab + 2 * r;
+    const T *const yt = ytab + 2 * r0;
 
     // ---- registers carried across planes ----
-    T t1c[V], t2c[V], t3c[V];    // T1..T3(n)
-    T t5m[V], t6m[V];            // T5(n-1), T6(n-1)
-    T t3R = (T)0;                // T3(n, j, kR) for lane 31
-    const T *rowc[V];            // class rows (coefficients) of this thread's cells at plane n
+    T t1c[RW][V], t2c[RW][V], t3c[RW][V];    // T1..T3(n)
+    T t5m[RW][V], t6m[RW][V];                // T5(n-1), T6(n-1)
+    T t3R[RW];                               // T3(n, j, kR) for lane 31
+    const T *rowc[RW][V];                    // class rows (coefficients) of this thread's cells at plane n
 #pragma unroll
-    for (int e = 0; e < V; ++e) { t1c[e] = t2c[e] = t3c[e] = t5m[e] = t6m[e] = (T)0; rowc[e] = stab; }
+    for (int q = 0; q < RW; ++q) {
+        t3R[q] = (T)0;
+#pragma unroll
+        for (int e = 0; e < V; ++e) { t1c[q][e] = t2c[q][e] = t3c[q][e] = t5m[q][e] = t6m[q][e] = (T)0; rowc[q][e] = stab; }
+    }
 
     // element offset of (plane n, j, kb) in a displacement array (the host guarantees it fits 31 bits)
     int off = (int)((long long)lbase * g.ps + (long long)j * g.nzp + kb);
     const int dps = (int)g.ps;
 
-    mbar_wait(bar_full, 0);                           // plane q = 0 (n = ia - 1)
+    if (PHB_DIAG != 2) mbar_wait(bar_full, 0);        // plane q = 0 (n = ia - 1)
     int sCi = 0, sNi = 1 % NST;                       // stage indices of plane n and n + 1
     uint32_t phN = 0;                                 // phase parity of full[sNi] for plane n + 1
 
-    constexpr int kUnroll = PHB_UNROLL;
+    constexpr int kUnroll = (RW == 1) ? PHB_UNROLL : 1;
 #pragma unroll kUnroll
     for (int it = 0; it + 1 < nplanes; ++it) {
         const int n = ia - 1 + it;                    // plane being completed; n + 1 is the newest
@@ -344,206 +381,292 @@ k_step_march(const __grid_constant__ MarchMaps tm, StepArgs<typename A::T> p, Ma
         const T *const uN = reinterpret_cast<const T *>(sm + sNi * C_::STAGE);     // plane n+1 tiles
         auto vec = [](const T *q) -> PV { return *reinterpret_cast<const PV *>(q); };
 
-        mbar_wait(bar_full + sNi * 8, phN);
+        if (PHB_DIAG != 2) mbar_wait(bar_full + sNi * 8, phN);
 
         // per-plane x spacings (uniform); element 0 of the k0c thread uses the first elements (App. B #1, #2)
         const T sfx_n = sxp[2 * (it + 1) + 0];        // fdx[n]
         const T ssx_n = sxp[2 * (it + 1) + 1];        // sdx[n]   = sdx[(n+1)-1]
         const T ssx_m = sxp[2 * it + 1];              // sdx[n-1]
-        const T sfy = yt[0], ssy = yt[1];             // fdy[j], sdy[j-1]
         const PV zf = vec(zt), zs = vec(zt + TZ);     // fdz[k], sdz[k-1] (k = 0: sdz[0])
 
+        // With several rows per warp every phase below is ONE basic block over all rows (no per-row branches), so
+        // the rows' independent dependency chains interleave; halo rows then compute values nobody reads and only
+        // the stores are predicated.  With one row per warp the halo-row warps skip the dead phases instead.
         // (1) shear stresses at plane n
-        T t4[V], t5[V], t6[V];
-        T t4L = (T)0, t5L = (T)0;
-        const PV uxc = vec(uC + eo), uyc = vec(uC + UCE + eo), uzc = vec(uC + 2 * UCE + eo);
+        T t4[RW][V], t5[RW][V], t6[RW][V];
+        T t4L[RW], t5L[RW];
+        PV uxc[RW], uyc[RW], uzc[RW];
 #pragma unroll
-        for (int e = 0; e < V; ++e) t4[e] = t5[e] = t6[e] = (T)0;
-        if (it == 0 || !need_normal) {   // (the bottom halo row never runs the normal-stress phase that carries the rows)
-            const CW cwc = *reinterpret_cast<const CW *>(sm + sCi * C_::STAGE + C_::OFF_C + r * C_::CB + 16 + lane * V);
+        for (int q = 0; q < RW; ++q) {
+            uxc[q] = vec(uC + eo + q * ROWE); uyc[q] = vec(uC + UCE + eo + q * ROWE); uzc[q] = vec(uC + 2 * UCE + eo + q * ROWE);
+            t4L[q] = t5L[q] = (T)0;
 #pragma unroll
-            for (int e = 0; e < V; ++e) rowc[e] = stab + (int)((cwc >> (8 * e)) & 255u) * CLS_W;
+            for (int e = 0; e < V; ++e) t4[q][e] = t5[q][e] = t6[q][e] = (T)0;
         }
-        if (need_shear) {
-            const PV uyn = vec(uN + UCE + eo), uzn = vec(uN + 2 * UCE + eo);
-            const PV uzN = vec(uC + 2 * UCE + eo + eN), uxN = vec(uC + eo + eN);     // uz(n, j+1), ux(n, j+1)
-            T uyE = shfl_dn1(uyc.v[0]), uxE = shfl_dn1(uxc.v[0]);                    // uy(n, k+1), ux(n, k+1)
-            if (lane == 31) { uyE = uC[UCE + r * ROWE + 33 * V]; uxE = uC[r * ROWE + 33 * V]; }
-            const T shb0 = k0c ? g.fdz0 : sfx_n;       // T5, T6 second term on k = 0: fdz[0]
+        if (it == 0 || (RW == 1 && !need_normal[0])) {   // (with one row per warp the bottom halo row never runs the normal-stress phase that carries the rows)
 #pragma unroll
-            for (int e = 0; e < V; ++e) {
-                const T uye = (e == V - 1) ? uyE : uyc.v[e < V - 1 ? e + 1 : e];
-                const T uxe = (e == V - 1) ? uxE : uxc.v[e < V - 1 ? e + 1 : e];
-                const T *c = rowc[e];
-                const bool k0 = (e == 0) && k0c;
-                const T shb = (e == 0) ? shb0 : sfx_n;
-                t4[e] = shear<A>(c[CLS_C44], A::sub(uye, uyc.v[e]), k0 ? g.fdy0 : zf.v[e],
-                                 A::sub(uzN.v[e], uzc.v[e]), k0 ? g.fdz0 : sfy);
-                t5[e] = shear<A>(c[CLS_C55], A::sub(uxe, uxc.v[e]), k0 ? g.fdx0 : zf.v[e],
-                                 A::sub(uzn.v[e], uzc.v[e]), shb);
-                t6[e] = shear<A>(c[CLS_C66], A::sub(uxN.v[e], uxc.v[e]), k0 ? g.fdx0 : sfy,
-                                 A::sub(uyn.v[e], uyc.v[e]), shb);
+            for (int q = 0; q < RW; ++q) {
+                const CW cwc = *reinterpret_cast<const CW *>(sm + sCi * C_::STAGE + C_::OFF_C + (r0 + q) * C_::CB + 16 + lane * V);
+#pragma unroll
+                for (int e = 0; e < V; ++e) rowc[q][e] = stab + (int)((cwc >> (8 * e)) & kClsMask) * CLS_W;
             }
-            if (haveL) {   // T4, T5 at (n, j, kL) for the first element's uy / ux update (never k = 0)
-                const T *c = stab + (int)sm[sCi * C_::STAGE + C_::OFF_C + r * C_::CB + 15] * CLS_W;
-                const T *h = uC + r * ROWE + V - 1;
-                const T uxL = h[0], uyL = h[UCE], uzL = h[2 * UCE], uzLN = h[2 * UCE + eN];
-                const T uzLn = uN[2 * UCE + r * ROWE + V - 1];
-                const T sfzL = g.fdz[k0t - 1];
-                t4L = shear<A>(c[CLS_C44], A::sub(uyc.v[0], uyL), sfzL, A::sub(uzLN, uzL), sfy);
-                t5L = shear<A>(c[CLS_C55], A::sub(uxc.v[0], uxL), sfzL, A::sub(uzLn, uzL), sfx_n);
+        }
+        if ((RW > 1 || need_shear[0]) && PHB_DIAG != 1) {
+            const T shb0 = k0c ? g.fdz0 : sfx_n;       // T5, T6 second term on k = 0: fdz[0]
+            PV uyn[RW], uzn[RW], uzN[RW], uxN[RW];
+            T uyE[RW], uxE[RW];
+#pragma unroll
+            for (int q = 0; q < RW; ++q) {
+                uyn[q] = vec(uN + UCE + eo + q * ROWE); uzn[q] = vec(uN + 2 * UCE + eo + q * ROWE);
+                // uz(n, j+1), ux(n, j+1): the warp's own next row, or the ring row above its last row
+                uzN[q] = (q < RW - 1) ? uzc[q < RW - 1 ? q + 1 : q] : vec(uC + 2 * UCE + eo + q * ROWE + eN);
+                uxN[q] = (q < RW - 1) ? uxc[q < RW - 1 ? q + 1 : q] : vec(uC + eo + q * ROWE + eN);
+                const T hy = uC[UCE + (r0 + q) * ROWE + 33 * V], hx = uC[(r0 + q) * ROWE + 33 * V];   // ring halo column kR (broadcast)
+                const T sy_ = shfl_dn1(uyc[q].v[0]), sx_ = shfl_dn1(uxc[q].v[0]);                        // uy(n, k+1), ux(n, k+1)
+                uyE[q] = (lane == 31) ? hy : sy_;
+                uxE[q] = (lane == 31) ? hx : sx_;
+            }
+#pragma unroll
+            for (int q = 0; q < RW; ++q) {
+                const T sfy = yt[2 * q];
+#pragma unroll
+                for (int e = 0; e < V; ++e) {
+                    const T uye = (e == V - 1) ? uyE[q] : uyc[q].v[e < V - 1 ? e + 1 : e];
+                    const T uxe = (e == V - 1) ? uxE[q] : uxc[q].v[e < V - 1 ? e + 1 : e];
+                    const T *c = rowc[q][e];
+                    const bool k0 = (e == 0) && k0c;
+                    const T shb = (e == 0) ? shb0 : sfx_n;
+                    t4[q][e] = shear<A>(c[CLS_C44], A::sub(uye, uyc[q].v[e]), k0 ? g.fdy0 : zf.v[e],
+                                        A::sub(uzN[q].v[e], uzc[q].v[e]), k0 ? g.fdz0 : sfy);
+                    t5[q][e] = shear<A>(c[CLS_C55], A::sub(uxe, uxc[q].v[e]), k0 ? g.fdx0 : zf.v[e],
+                                        A::sub(uzn[q].v[e], uzc[q].v[e]), shb);
+                    t6[q][e] = shear<A>(c[CLS_C66], A::sub(uxN[q].v[e], uxc[q].v[e]), k0 ? g.fdx0 : sfy,
+                                        A::sub(uyn[q].v[e], uyc[q].v[e]), shb);
+                }
+            }
+            if (haveL && (RW > 1 || row_out[0])) {   // T4, T5 at (n, j, kL) for the first element's uy / ux update (never k = 0)
+                const T sfzL = ytab[2 * R];
+#pragma unroll
+                for (int q = 0; q < RW; ++q) {
+                    const T *c = stab + (int)(sm[sCi * C_::STAGE + C_::OFF_C + (r0 + q) * C_::CB + 15] & kClsMask) * CLS_W;
+                    const T *h = uC + (r0 + q) * ROWE + V - 1;
+                    const int hN = (q < RW - 1) ? ROWE : eN;
+                    const T uxL = h[0], uyL = h[UCE], uzL = h[2 * UCE], uzLN = h[2 * UCE + hN];
+                    const T uzLn = uN[2 * UCE + (r0 + q) * ROWE + V - 1];
+                    t4L[q] = shear<A>(c[CLS_C44], A::sub(uyc[q].v[0], uyL), sfzL, A::sub(uzLN, uzL), yt[2 * q]);
+                    t5L[q] = shear<A>(c[CLS_C55], A::sub(uxc[q].v[0], uxL), sfzL, A::sub(uzLn, uzL), sfx_n);
+                }
             }
         }
 
-        // (2) publish T2(n), T4(n), T6(n) for the y-neighbours and signal them
+        // (2) publish T2(n) of the warp's first row and T4(n), T6(n) of its last row for the y-neighbours and signal them
         T *const xb = reinterpret_cast<T *>(sm + C_::OFF_X + (it & 1) * C_::XBUF) + xo;
-        {
+        if (PHB_DIAG != 1) {
             PV a, b, c;
 #pragma unroll
-            for (int e = 0; e < V; ++e) { a.v[e] = t2c[e]; b.v[e] = t4[e]; c.v[e] = t6[e]; }
+            for (int e = 0; e < V; ++e) { a.v[e] = t2c[0][e]; b.v[e] = t4[RW - 1][e]; c.v[e] = t6[RW - 1][e]; }
             *reinterpret_cast<PV *>(xb) = a;
             *reinterpret_cast<PV *>(xb + XCE) = b;
             *reinterpret_cast<PV *>(xb + 2 * XCE) = c;
         }
         __syncwarp();
         // tell both neighbours (arrive on THEIR barrier): each warp then waits on one barrier only
-        if (lane == 0 && r >= 1) mbar_arrive(pubO - 16 + (it & 1) * 8);
-        if (lane == 1 && r <= R - 2) mbar_arrive(pubO + 16 + (it & 1) * 8);
+        if (lane == 0 && w >= 1 && PHB_DIAG != 1) mbar_arrive(pubO - 16 + (it & 1) * 8);
+        if (lane == 1 && w <= W - 2 && PHB_DIAG != 1) mbar_arrive(pubO + 16 + (it & 1) * 8);
 
         // (3) normal stresses at plane n + 1 (overlaps the neighbours' publishing)
-        T t1n[V], t2n[V], t3n[V];
-        T t3Rn = (T)0;
-        const T *rown[V];
+        T t1n[RW][V], t2n[RW][V], t3n[RW][V];
+        T t3Rn[RW];
+        const T *rown[RW][V];
 #pragma unroll
-        for (int e = 0; e < V; ++e) { t1n[e] = t2n[e] = t3n[e] = (T)0; rown[e] = stab; }
-        if (need_normal) {
-            const PV uxn = vec(uN + eo), uyn = vec(uN + UCE + eo), uzn = vec(uN + 2 * UCE + eo);
-            const PV uyS = vec(uN + UCE + eo + eS);                              // uy(n+1, j-1)
-            T uzW0 = shfl_up1(uzn.v[V - 1]);                                     // uz(n+1, k-1) for element 0
-            if (lane == 0) uzW0 = uN[2 * UCE + r * ROWE + V - 1];                // ring halo (0 below k = 0)
-            const CW cwn = *reinterpret_cast<const CW *>(sm + sNi * C_::STAGE + C_::OFF_C + r * C_::CB + 16 + lane * V);
+        for (int q = 0; q < RW; ++q) {
+            t3Rn[q] = (T)0;
 #pragma unroll
-            for (int e = 0; e < V; ++e) {
-                const bool k0 = (e == 0) && k0c;
-                const T dxx = A::sub(uxn.v[e], uxc.v[e]);
-                const T dyy = A::sub(uyn.v[e], uyS.v[e]);
-                const T dzz = A::sub(uzn.v[e], (e == 0) ? uzW0 : uzn.v[e > 0 ? e - 1 : 0]);
-                const T sx = k0 ? g.sdx0 : ssx_n, sy = k0 ? g.sdy0 : ssy;
-                const T *c = rown[e] = stab + (int)((cwn >> (8 * e)) & 255u) * CLS_W;
-                if constexpr (A::EXACT) {
-                    t1n[e] = normal_row<A>(c + 0, dxx, dyy, dzz, sx, sy, zs.v[e]);
-                    t2n[e] = normal_row<A>(c + 3, dxx, dyy, dzz, sx, sy, zs.v[e]);
-                    t3n[e] = normal_row<A>(c + 6, dxx, dyy, dzz, sx, sy, zs.v[e]);
-                } else {   // FAST: the three rows share the scaled strains (spacing tables hold reciprocals)
-                    const T ex = dxx * sx, ey = dyy * sy, ez = dzz * zs.v[e];
-                    t1n[e] = c[0] * ex + c[1] * ey + c[2] * ez;
-                    t2n[e] = c[3] * ex + c[4] * ey + c[5] * ez;
-                    t3n[e] = c[6] * ex + c[7] * ey + c[8] * ez;
+            for (int e = 0; e < V; ++e) { t1n[q][e] = t2n[q][e] = t3n[q][e] = (T)0; rown[q][e] = stab; }
+        }
+        if ((RW > 1 || need_normal[0]) && PHB_DIAG != 1) {
+            PV uxn[RW], uyn[RW], uzn[RW], uyS[RW];
+            T uzW0[RW];
+            CW cwn[RW];
+#pragma unroll
+            for (int q = 0; q < RW; ++q) {
+                uxn[q] = vec(uN + eo + q * ROWE); uyn[q] = vec(uN + UCE + eo + q * ROWE); uzn[q] = vec(uN + 2 * UCE + eo + q * ROWE);
+                cwn[q] = *reinterpret_cast<const CW *>(sm + sNi * C_::STAGE + C_::OFF_C + (r0 + q) * C_::CB + 16 + lane * V);
+            }
+#pragma unroll
+            for (int q = 0; q < RW; ++q) {
+                uyS[q] = (q >= 1) ? uyn[q >= 1 ? q - 1 : 0] : vec(uN + UCE + eo + eS);      // uy(n+1, j-1)
+                const T hz = uN[2 * UCE + (r0 + q) * ROWE + V - 1];                  // ring halo column kL (0 below k = 0)
+                const T sz_ = shfl_up1(uzn[q].v[V - 1]);                             // uz(n+1, k-1) for element 0
+                uzW0[q] = (lane == 0) ? hz : sz_;
+            }
+#pragma unroll
+            for (int q = 0; q < RW; ++q) {
+                const T ssy = yt[2 * q + 1];
+#pragma unroll
+                for (int e = 0; e < V; ++e) {
+                    const bool k0 = (e == 0) && k0c;
+                    const T dxx = A::sub(uxn[q].v[e], uxc[q].v[e]);
+                    const T dyy = A::sub(uyn[q].v[e], uyS[q].v[e]);
+                    const T dzz = A::sub(uzn[q].v[e], (e == 0) ? uzW0[q] : uzn[q].v[e > 0 ? e - 1 : 0]);
+                    const T sx = k0 ? g.sdx0 : ssx_n, sy = k0 ? g.sdy0 : ssy;
+                    const T *c = rown[q][e] = stab + (int)((cwn[q] >> (8 * e)) & kClsMask) * CLS_W;
+                    if constexpr (A::EXACT) {
+                        t1n[q][e] = normal_row<A>(c + 0, dxx, dyy, dzz, sx, sy, zs.v[e]);
+                        t2n[q][e] = normal_row<A>(c + 3, dxx, dyy, dzz, sx, sy, zs.v[e]);
+                        t3n[q][e] = normal_row<A>(c + 6, dxx, dyy, dzz, sx, sy, zs.v[e]);
+                    } else {   // FAST: the three rows share the scaled strains (spacing tables hold reciprocals)
+                        const T ex = dxx * sx, ey = dyy * sy, ez = dzz * zs.v[e];
+                        t1n[q][e] = c[0] * ex + c[1] * ey + c[2] * ez;
+                        t2n[q][e] = c[3] * ex + c[4] * ey + c[5] * ez;
+                        t3n[q][e] = c[6] * ex + c[7] * ey + c[8] * ez;
+                    }
                 }
             }
-            if (haveR) {   // T3(n+1, j, kR) for the next plane's uz update of the last element (never k = 0)
-                const T *c = stab + (int)sm[sNi * C_::STAGE + C_::OFF_C + r * C_::CB + 16 + TZ] * CLS_W;
-                const T *hC = uC + r * ROWE + 33 * V, *hN = uN + r * ROWE + 33 * V;
-                const T dxx = A::sub(hN[0], hC[0]);
-                const T dyy = A::sub(hN[UCE], hN[UCE + eS]);
-                const T dzz = A::sub(hN[2 * UCE], uzn.v[V - 1]);
-                t3Rn = normal_row<A>(c + 6, dxx, dyy, dzz, ssx_n, ssy, g.sdz[k0t + TZ - 1]);
+            if (haveR && (RW > 1 || row_out[0])) {   // T3(n+1, j, kR) for the next plane's uz update of the last element (never k = 0)
+                const T szR = ytab[2 * R + 1];
+#pragma unroll
+                for (int q = 0; q < RW; ++q) {
+                    const T *c = stab + (int)(sm[sNi * C_::STAGE + C_::OFF_C + (r0 + q) * C_::CB + 16 + TZ] & kClsMask) * CLS_W;
+                    const T *hC = uC + (r0 + q) * ROWE + 33 * V, *hN = uN + (r0 + q) * ROWE + 33 * V;
+                    const T dxx = A::sub(hN[0], hC[0]);
+                    const T dyy = A::sub(hN[UCE], hN[UCE + (q >= 1 ? -ROWE : eS)]);
+                    const T dzz = A::sub(hN[2 * UCE], uzn[q].v[V - 1]);
+                    t3Rn[q] = normal_row<A>(c + 6, dxx, dyy, dzz, ssx_n, yt[2 * q + 1], szR);
+                }
             }
         }
 
         // wait for both neighbours' plane-n stresses (also bounds the drift between warps)
-        mbar_wait(pubO + (it & 1) * 8, (it >> 1) & 1);
+        if (PHB_DIAG != 1) mbar_wait(pubO + (it & 1) * 8, (it >> 1) & 1);
 
-        if (emit && row_out) {
+        if (emit && any_out) {
+            if (PHB_DIAG != 2) mbar_wait(bar_fullO + (it % NSO) * 8, (uint32_t)(((it - 1) / NSO) & 1));   // planes 1, 2, ... use the ring
+            PV ox[RW], oy[RW], oz[RW];
+            PV dx[RW], dy[RW], dz[RW];                // COMP: new increments (stored in place of u_old)
             // (4) z-neighbour stresses
-            T t3U = shfl_dn1(t3c[0]);                 // T3(n, k+1) for element V-1
-            T t4W = shfl_up1(t4[V - 1]);              // T4(n, k-1) for element 0
-            T t5W = shfl_up1(t5[V - 1]);              // T5(n, k-1) for element 0
-            if (lane == 31) t3U = t3R;
-            if (lane == 0) { t4W = t4L; t5W = t5L; }  // zero below the k = 0 plane
-            mbar_wait(bar_fullO + (it % NSO) * 8, (uint32_t)(((it - 1) / NSO) & 1));   // planes 1, 2, ... use the ring
-            const T *const oC = reinterpret_cast<const T *>(sm + C_::OFF_O + (it % NSO) * C_::OSTAGE) + (r - 1) * TZ + lane * V;   // u_old(n)
-            PV ox, oy, oz;
-            PV dx, dy, dz;                            // COMP: new increments (stored in place of u_old)
-            {   // (5) ux
-                const PV t6S = vec(xb + 2 * XCE + xS), uo = vec(oC);
+            T t3U[RW], t4W[RW], t5W[RW];
 #pragma unroll
-                for (int e = 0; e < V; ++e) {
-                    const bool k0 = (e == 0) && k0c;
-                    const T *c = rowc[e];
-                    const T t5w = (e == 0) ? t5W : t5[e > 0 ? e - 1 : 0];
-                    const T acc = A::add(A::add(A::scl(A::sub(t1n[e], t1c[e]), k0 ? g.fdx0 : sfx_n),
-                                                A::scl(A::sub(t6[e], t6S.v[e]), k0 ? g.sdy0 : ssy)),
-                                         A::scl(A::sub(t5[e], t5w), zs.v[e]));
-                    if constexpr (A::COMP) { dx.v[e] = uo.v[e] + c[CLS_RX] * acc; ox.v[e] = uxc.v[e] + dx.v[e]; }
-                    else ox.v[e] = advance<A>(uxc.v[e], uo.v[e], c[CLS_RX], acc);
-                }
+            for (int q = 0; q < RW; ++q) {
+                const T a = shfl_dn1(t3c[q][0]);          // T3(n, k+1) for element V-1
+                const T b = shfl_up1(t4[q][V - 1]);       // T4(n, k-1) for element 0
+                const T c = shfl_up1(t5[q][V - 1]);       // T5(n, k-1) for element 0
+                t3U[q] = (lane == 31) ? t3R[q] : a;
+                t4W[q] = (lane == 0) ? t4L[q] : b;        // zero below the k = 0 plane
+                t5W[q] = (lane == 0) ? t5L[q] : c;
             }
-            {   // (6) uy
-                const PV t2N = vec(xb + xN), uo = vec(oC + OCE);
 #pragma unroll
-                for (int e = 0; e < V; ++e) {
-                    const bool k0 = (e == 0) && k0c;
-                    const T *c = rowc[e];
-                    const T t4w = (e == 0) ? t4W : t4[e > 0 ? e - 1 : 0];
-                    const T acc = A::add(A::add(A::scl(A::sub(t6[e], t6m[e]), k0 ? g.sdx0 : ssx_m),
-                                                A::scl(A::sub(t2N.v[e], t2c[e]), k0 ? g.fdy0 : sfy)),
-                                         A::scl(A::sub(t4[e], t4w), zs.v[e]));
-                    if constexpr (A::COMP) { dy.v[e] = uo.v[e] + c[CLS_RY] * acc; oy.v[e] = uyc.v[e] + dy.v[e]; }
-                    else oy.v[e] = advance<A>(uyc.v[e], uo.v[e], c[CLS_RY], acc);
+            for (int q = 0; q < RW; ++q) {
+                const T sfy = yt[2 * q], ssy = yt[2 * q + 1];                         // fdy[j], sdy[j-1]
+                const T *const oC = reinterpret_cast<const T *>(sm + C_::OFF_O + (it % NSO) * C_::OSTAGE) + (r0 + q - 1) * TZ + lane * V;   // u_old(n)
+                {   // (5) ux
+                    PV t6S;                               // T6(n, j-1): the warp's own previous row, or the neighbour warp's last row
+                    if (q >= 1) {
+#pragma unroll
+                        for (int e = 0; e < V; ++e) t6S.v[e] = t6[q >= 1 ? q - 1 : 0][e];
+                    } else t6S = vec(xb + 2 * XCE + xS);
+                    const PV uo = vec(oC);
+#pragma unroll
+                    for (int e = 0; e < V; ++e) {
+                        const bool k0 = (e == 0) && k0c;
+                        const T *c = rowc[q][e];
+                        const T t5w = (e == 0) ? t5W[q] : t5[q][e > 0 ? e - 1 : 0];
+                        const T acc = A::add(A::add(A::scl(A::sub(t1n[q][e], t1c[q][e]), k0 ? g.fdx0 : sfx_n),
+                                                    A::scl(A::sub(t6[q][e], t6S.v[e]), k0 ? g.sdy0 : ssy)),
+                                             A::scl(A::sub(t5[q][e], t5w), zs.v[e]));
+                        if constexpr (A::COMP) { dx[q].v[e] = uo.v[e] + c[CLS_RX] * acc; ox[q].v[e] = uxc[q].v[e] + dx[q].v[e]; }
+                        else ox[q].v[e] = advance<A>(uxc[q].v[e], uo.v[e], c[CLS_RX], acc);
+                    }
                 }
-            }
-            {   // (7) uz   (k = 0: "+ T3[..,1] - T3[..,0]/fdz[0]", T3[..,1] NOT divided, App. B #3)
-                const PV t4S = vec(xb + XCE + xS), uo = vec(oC + 2 * OCE);
+                {   // (6) uy
+                    PV t2N;                               // T2(n, j+1): the warp's own next row, or the neighbour warp's first row
+                    if (q < RW - 1) {
 #pragma unroll
-                for (int e = 0; e < V; ++e) {
-                    const bool k0 = (e == 0) && k0c;
-                    const T *c = rowc[e];
-                    const T t3u = (e == V - 1) ? t3U : t3c[e < V - 1 ? e + 1 : e];
-                    const T acc = A::add(A::add(A::scl(A::sub(t5[e], t5m[e]), k0 ? g.sdx0 : ssx_m),
-                                                A::scl(A::sub(t4[e], t4S.v[e]), k0 ? g.sdy0 : ssy)),
-                                         A::scl(A::sub(t3u, t3c[e]), k0 ? (T)1 : zf.v[e]));
-                    if constexpr (A::COMP) { dz.v[e] = uo.v[e] + c[CLS_RZ] * acc; oz.v[e] = uzc.v[e] + dz.v[e]; }
-                    else oz.v[e] = advance<A>(uzc.v[e], uo.v[e], c[CLS_RZ], acc);
+                        for (int e = 0; e < V; ++e) t2N.v[e] = t2c[q < RW - 1 ? q + 1 : q][e];
+                    } else t2N = vec(xb + xN);
+                    const PV uo = vec(oC + OCE);
+#pragma unroll
+                    for (int e = 0; e < V; ++e) {
+                        const bool k0 = (e == 0) && k0c;
+                        const T *c = rowc[q][e];
+                        const T t4w = (e == 0) ? t4W[q] : t4[q][e > 0 ? e - 1 : 0];
+                        const T acc = A::add(A::add(A::scl(A::sub(t6[q][e], t6m[q][e]), k0 ? g.sdx0 : ssx_m),
+                                                    A::scl(A::sub(t2N.v[e], t2c[q][e]), k0 ? g.fdy0 : sfy)),
+                                             A::scl(A::sub(t4[q][e], t4w), zs.v[e]));
+                        if constexpr (A::COMP) { dy[q].v[e] = uo.v[e] + c[CLS_RY] * acc; oy[q].v[e] = uyc[q].v[e] + dy[q].v[e]; }
+                        else oy[q].v[e] = advance<A>(uyc[q].v[e], uo.v[e], c[CLS_RY], acc);
+                    }
+                }
+                {   // (7) uz   (k = 0: "+ T3[..,1] - T3[..,0]/fdz[0]", T3[..,1] NOT divided, App. B #3)
+                    PV t4S;
+                    if (q >= 1) {
+#pragma unroll
+                        for (int e = 0; e < V; ++e) t4S.v[e] = t4[q >= 1 ? q - 1 : 0][e];
+                    } else t4S = vec(xb + XCE + xS);
+                    const PV uo = vec(oC + 2 * OCE);
+#pragma unroll
+                    for (int e = 0; e < V; ++e) {
+                        const bool k0 = (e == 0) && k0c;
+                        const T *c = rowc[q][e];
+                        const T t3u = (e == V - 1) ? t3U[q] : t3c[q][e < V - 1 ? e + 1 : e];
+                        const T acc = A::add(A::add(A::scl(A::sub(t5[q][e], t5m[q][e]), k0 ? g.sdx0 : ssx_m),
+                                                    A::scl(A::sub(t4[q][e], t4S.v[e]), k0 ? g.sdy0 : ssy)),
+                                             A::scl(A::sub(t3u, t3c[q][e]), k0 ? (T)1 : zf.v[e]));
+                        if constexpr (A::COMP) { dz[q].v[e] = uo.v[e] + c[CLS_RZ] * acc; oz[q].v[e] = uzc[q].v[e] + dz[q].v[e]; }
+                        else oz[q].v[e] = advance<A>(uzc[q].v[e], uo.v[e], c[CLS_RZ], acc);
+                    }
                 }
             }
             // i = 0: uy, uz keep u_new == u (App. B #9); uz(0, j, 0) is the pre-source value
             if (n == 0) {
-                oy = uyc;
-                oz = uzc;
-                if (k0c && p.line_save) oz.v[0] = p.line_save[j];
-                if constexpr (A::COMP) {      // keep delta = u_new - u here too (only matters for reading u_old back)
 #pragma unroll
-                    for (int e = 0; e < V; ++e) { dy.v[e] = (T)0; dz.v[e] = oz.v[e] - uzc.v[e]; }
+                for (int q = 0; q < RW; ++q) {
+                    oy[q] = uyc[q];
+                    oz[q] = uzc[q];
+                    if (k0c && p.line_save && row_out[q]) oz[q].v[0] = p.line_save[j + q];
+                    if constexpr (A::COMP) {      // keep delta = u_new - u here too (only matters for reading u_old back)
+#pragma unroll
+                        for (int e = 0; e < V; ++e) { dy[q].v[e] = (T)0; dz[q].v[e] = oz[q].v[e] - uzc[q].v[e]; }
+                    }
                 }
             }
-            if constexpr (A::COMP) {
-                if (in_box) {     // the u_old tile of this plane was read by TMA before: in-place update of delta
-                    *reinterpret_cast<PV *>(p.old.ux + off) = dx;
-                    *reinterpret_cast<PV *>(p.old.uy + off) = dy;
-                    *reinterpret_cast<PV *>(p.old.uz + off) = dz;
+#pragma unroll
+            for (int q = 0; q < RW; ++q) {
+                const int offq = off + q * g.nzp;
+                const bool st = in_box[q] && row_out[q];
+                if constexpr (A::COMP) {
+                    if (st) {     // the u_old tile of this plane was read by TMA before: in-place update of delta
+                        *reinterpret_cast<PV *>(p.old.ux + offq) = dx[q];
+                        *reinterpret_cast<PV *>(p.old.uy + offq) = dy[q];
+                        *reinterpret_cast<PV *>(p.old.uz + offq) = dz[q];
+                    }
+                }
+                if (st) {
+                    *reinterpret_cast<PV *>(p.nw.ux + offq) = ox[q];
+                    *reinterpret_cast<PV *>(p.nw.uy + offq) = oy[q];
+                    *reinterpret_cast<PV *>(p.nw.uz + offq) = oz[q];
                 }
             }
-            if (in_box) {
-                *reinterpret_cast<PV *>(p.nw.ux + off) = ox;
-                *reinterpret_cast<PV *>(p.nw.uy + off) = oy;
-                *reinterpret_cast<PV *>(p.nw.uz + off) = oz;
-                // fused halo exchange: the slab's edge planes go straight into the neighbours' ghost planes over NVLink
-                if constexpr (PUSH) {
-                if (n == g.x0 && p.push_lo[0]) {
-                    const int po = j * g.nzp + kb;
-                    *reinterpret_cast<PV *>(p.push_lo[0] + po) = ox;
-                    *reinterpret_cast<PV *>(p.push_lo[1] + po) = oy;
-                    *reinterpret_cast<PV *>(p.push_lo[2] + po) = oz;
-                    __threadfence_system();       // out before the stream-ordered flag write that follows the kernel
-                }
-                if (n == g.x0 + g.nxl - 1 && p.push_hi[0]) {
-                    const int po = j * g.nzp + kb;
-                    *reinterpret_cast<PV *>(p.push_hi[0] + po) = ox;
-                    *reinterpret_cast<PV *>(p.push_hi[1] + po) = oy;
-                    *reinterpret_cast<PV *>(p.push_hi[2] + po) = oz;
-                    __threadfence_system();
-                }
+            // fused halo exchange: the slab's edge planes go straight into the neighbours' ghost planes over NVLink
+            if constexpr (PUSH) {
+                const bool lo = (n == g.x0 && p.push_lo[0]), hi = (n == g.x0 + g.nxl - 1 && p.push_hi[0]);
+                if (lo || hi) {
+#pragma unroll
+                    for (int q = 0; q < RW; ++q) {
+                        if (!(in_box[q] && row_out[q])) continue;
+                        const int po = (j + q) * g.nzp + kb;
+                        if (lo) {
+                            *reinterpret_cast<PV *>(p.push_lo[0] + po) = ox[q];
+                            *reinterpret_cast<PV *>(p.push_lo[1] + po) = oy[q];
+                            *reinterpret_cast<PV *>(p.push_lo[2] + po) = oz[q];
+                        }
+                        if (hi) {
+                            *reinterpret_cast<PV *>(p.push_hi[0] + po) = ox[q];
+                            *reinterpret_cast<PV *>(p.push_hi[1] + po) = oy[q];
+                            *reinterpret_cast<PV *>(p.push_hi[2] + po) = oz[q];
+                        }
+                        __threadfence_system();       // out before the stream-ordered flag write that follows the kernel
+                    }
                 }
             }
         }
@@ -562,12 +685,18 @@ k_step_march(const __grid_constant__ MarchMaps tm, StepArgs<typename A::T> p, Ma
         }
 
         // (8) rotate
-        t3R = t3Rn;
         off += dps;
         sCi = sNi;
         if (++sNi == NST) { sNi = 0; phN ^= 1u; }
 #pragma unroll
-        for (int e = 0; e < V; ++e) { t1c[e] = t1n[e]; t2c[e] = t2n[e]; t3c[e] = t3n[e]; t5m[e] = t5[e]; t6m[e] = t6[e]; rowc[e] = rown[e]; }
+        for (int q = 0; q < RW; ++q) {
+            t3R[q] = t3Rn[q];
+#pragma unroll
+            for (int e = 0; e < V; ++e) {
+                t1c[q][e] = t1n[q][e]; t2c[q][e] = t2n[q][e]; t3c[q][e] = t3n[q][e];
+                t5m[q][e] = t5[q][e]; t6m[q][e] = t6[q][e]; rowc[q][e] = rown[q][e];
+            }
+        }
     }
 }
 
@@ -628,15 +757,15 @@ inline bool make_class_map(CUtensorMap *tm, void *base, int nzp, int ny, int pla
 template <class T> inline const char *march_name() { return "march_tma"; }
 
 // returns launches made (1), 0 for an empty range, -1 if the shared-memory request is refused
-template <class A, int R, int NST, bool PUSH = false>
+template <class A, int R, int NST, int RW = 1, bool PUSH = false>
 inline int launch_march_cfg(const StepArgs<typename A::T> &p, const MatCls<typename A::T> &m, const MarchMaps &maps,
                             int chunks, cudaStream_t st) {
     using T = typename A::T;
-    using C_ = MarchCfg<T, R, NST>;
+    using C_ = MarchCfg<T, R, NST, RW>;
     if constexpr (!PUSH) {
-        if (p.push_lo[0] || p.push_hi[0]) return launch_march_cfg<A, R, NST, true>(p, m, maps, chunks, st);
+        if (p.push_lo[0] || p.push_hi[0]) return launch_march_cfg<A, R, NST, RW, true>(p, m, maps, chunks, st);
     }
-    auto kern = k_step_march<A, R, NST, PUSH>;
+    auto kern = k_step_march<A, R, NST, PUSH, RW>;
     static size_t attr_by_dev[64] = {};   // per template instantiation and device (the attribute is per device)
     int dev = 0;
     cudaGetDevice(&dev);
@@ -655,7 +784,7 @@ inline int launch_march_cfg(const StepArgs<typename A::T> &p, const MatCls<typen
         attr_bytes = smem;
     }
     dim3 grid((p.g.nzp + C_::TZ - 1) / C_::TZ, (p.g.ny + C_::TY - 1) / C_::TY, p.edge_b >= 0 ? 2 : (np + chunk - 1) / chunk);
-    kern<<<grid, R * 32, smem, st>>>(maps, p, m, chunk);
+    kern<<<grid, C_::W * 32, smem, st>>>(maps, p, m, chunk);
     return 1;
 }
 

@@ -19,6 +19,9 @@
 #include <thread>
 #include <vector>
 
+#ifndef PHB_DEFAULT_RW
+#define PHB_DEFAULT_RW 1   // rows per warp of the marching kernel (PHB_MARCH_RW overrides at run time)
+#endif
 #include "fd_common.cuh"
 #include "k_boundary.cuh"
 #include "k_march.cuh"
@@ -161,7 +164,7 @@ struct phb_ctx {
     // marching kernel: TMA descriptors per [buffer][component], tile plan
     MarchMaps mm[3];           // indexed by the buffer that holds u_cur
     bool maps_ok = false;
-    int mR = 16, mNST = 4, mChunks = 0;
+    int mR = 16, mNST = 4, mRW = PHB_DEFAULT_RW, mChunks = 0;   // marching kernel: tile rows, u_cur ring depth, rows per warp
     // per-kernel timing of the stencil launches (bench roofline): event pairs on the launch stream
     bool prof = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_ev;
@@ -466,7 +469,8 @@ struct Engine : IEngine {
                 const MarchMaps &mp = c->mm[b_cur()];
                 const int ch = plan_chunks(ie - ib);
                 int r = -2;
-                if (c->mR == 16 && c->mNST == 4) r = launch_march_cfg<A, 16, 4>(p, m, mp, ch, c->st);
+                if (c->mR == 16 && c->mNST == 4 && c->mRW == 2) r = launch_march_cfg<A, 16, 4, 2>(p, m, mp, ch, c->st);
+                else if (c->mR == 16 && c->mNST == 4) r = launch_march_cfg<A, 16, 4>(p, m, mp, ch, c->st);
                 else if (c->mR == 16 && c->mNST == 3) r = launch_march_cfg<A, 16, 3>(p, m, mp, ch, c->st);
                 else if (c->mR == 8 && c->mNST == 4) r = launch_march_cfg<A, 8, 4>(p, m, mp, ch, c->st);
                 if (r == -2) return fail("no marching-kernel instantiation for R=%d NST=%d", c->mR, c->mNST);
@@ -822,6 +826,8 @@ int phb_create(const phb_cfg *cfg, phb_ctx **out) {
     if (cfg->dtype == PHB_F64) c->eng = new Engine<double>(c); else c->eng = new Engine<float>(c);
     if (const char *e = getenv("PHB_MARCH_R")) c->mR = atoi(e);
     if (const char *e = getenv("PHB_MARCH_NST")) c->mNST = atoi(e);
+    if (const char *e = getenv("PHB_MARCH_RW")) c->mRW = atoi(e);
+    if (c->mRW != 1 && !(c->mRW == 2 && c->mR == 16 && c->mNST == 4)) c->mRW = 1;   // two rows per warp exist for R = 16, NST = 4
     if (const char *e = getenv("PHB_MARCH_CHUNKS")) c->mChunks = atoi(e);
     if (c->mR != 8 && c->mR != 16) return cleanup(fail("PHB_MARCH_R must be 8 or 16"));
     // recorder ring
