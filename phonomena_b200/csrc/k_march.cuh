@@ -45,6 +45,9 @@
 #ifndef PHB_UNROLL
 #define PHB_UNROLL 2
 #endif
+#ifndef PHB_UNROLL_RW2
+#define PHB_UNROLL_RW2 2
+#endif
 #ifndef PHB_NSO_RW2
 #define PHB_NSO_RW2 3
 #endif
@@ -55,6 +58,11 @@
 //                  exchange and stores run -> the rate the per-warp dependency chains allow
 #ifndef PHB_DIAG
 #define PHB_DIAG 0
+#endif
+// who refills the TMA rings: 1 = round robin over the warps, mid-iteration (see the plane loop); 0 = whichever warp
+// finds a `done` phase complete after its own arrival (barrier test + CAS in every warp at the end of every plane)
+#ifndef PHB_REFILL
+#define PHB_REFILL 1
 #endif
 
 namespace phb {
@@ -372,7 +380,7 @@ k_step_march(const __grid_constant__ MarchMaps tm, StepArgs<typename A::T> p, Ma
     int sCi = 0, sNi = 1 % NST;                       // stage indices of plane n and n + 1
     uint32_t phN = 0;                                 // phase parity of full[sNi] for plane n + 1
 
-    constexpr int kUnroll = (RW == 1) ? PHB_UNROLL : 1;
+    constexpr int kUnroll = (RW == 1) ? PHB_UNROLL : PHB_UNROLL_RW2;
 #pragma unroll kUnroll
     for (int it = 0; it + 1 < nplanes; ++it) {
         const int n = ia - 1 + it;                    // plane being completed; n + 1 is the newest
@@ -473,6 +481,19 @@ k_step_march(const __grid_constant__ MarchMaps tm, StepArgs<typename A::T> p, Ma
         // tell both neighbours (arrive on THEIR barrier): each warp then waits on one barrier only
         if (lane == 0 && w >= 1 && PHB_DIAG != 1) mbar_arrive(pubO - 16 + (it & 1) * 8);
         if (lane == 1 && w <= W - 2 && PHB_DIAG != 1) mbar_arrive(pubO + 16 + (it & 1) * 8);
+#if PHB_REFILL == 1
+        // Ring refill, round robin: in iteration `it` warp it % W reloads the stage that plane it - 1 occupied (claim
+        // it - 1 + NST).  It does so here, between its publish and its neighbour wait, where a warp has slack, and it
+        // waits for a `done` phase that normally completed long ago -- so no warp tests a barrier or touches a counter
+        // at the end of its iteration, and the extra work never lands on the warp that is already last.
+        if (PHB_DIAG != 2 && it >= 1 && w == (it & (W - 1)) && it - 1 + NST < nclaims) {
+            if (lane == 0) {
+                mbar_wait(bar_empty + ((it - 1) % NST) * 8, (uint32_t)(((it - 1) / NST) & 1));
+                issue(it - 1 + NST);
+            }
+            __syncwarp();
+        }
+#endif
 
         // (3) normal stresses at plane n + 1 (overlaps the neighbours' publishing)
         T t1n[RW][V], t2n[RW][V], t3n[RW][V];
@@ -674,6 +695,7 @@ k_step_march(const __grid_constant__ MarchMaps tm, StepArgs<typename A::T> p, Ma
         __syncwarp();
         if (lane == 0) {
             mbar_arrive(bar_empty + sCi * 8);
+#if PHB_REFILL == 0
             // refill every stage whose readers are all done (usually the one just released by the
             // slowest warp of plane `it`)
             for (;;) {
@@ -682,6 +704,7 @@ k_step_march(const __grid_constant__ MarchMaps tm, StepArgs<typename A::T> p, Ma
                 if (!mbar_test(bar_empty + (q % NST) * 8, (uint32_t)((q / NST - 1) & 1))) break;
                 if (atomicCAS(issued, q, q + 1) == q) issue(q);
             }
+#endif
         }
 
         // (8) rotate

@@ -20,7 +20,7 @@
 #include <vector>
 
 #ifndef PHB_DEFAULT_RW
-#define PHB_DEFAULT_RW 1   // rows per warp of the marching kernel (PHB_MARCH_RW overrides at run time)
+#define PHB_DEFAULT_RW 2   // rows per warp of the marching kernel (PHB_MARCH_RW overrides at run time)
 #endif
 #include "fd_common.cuh"
 #include "k_boundary.cuh"
