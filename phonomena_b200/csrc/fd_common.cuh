@@ -130,6 +130,12 @@ __device__ __forceinline__ typename A::T shear(typename A::T c, typename A::T a,
                                                typename A::T b, typename A::T sb) {
     return A::mul(c, A::add(A::scl(a, sa), A::scl(b, sb)));
 }
+// first-order Mur face: q_new[face] = q[inner] + c * (q_new[inner] - q[face])   (base_solver.py:539-554, App. A.5)
+template <class A>
+__device__ __forceinline__ typename A::T mur(typename A::T q_inner, typename A::T qn_inner, typename A::T q_face,
+                                             typename A::T c) {
+    return A::add(q_inner, A::mul(c, A::sub(qn_inner, q_face)));
+}
 // u_new = 2u - u_old + (d2/rho) * acc                          (base_solver.py:441-463,495-517)
 template <class A>
 __device__ __forceinline__ typename A::T advance(typename A::T u, typename A::T uo, typename A::T rinv,

@@ -26,11 +26,6 @@ __global__ void k_source(Geo<T> g, T *uz_cur, T *line_save, const double *w, lon
 // launches them in that order on one stream.
 // Per component: extent (ex, ey, ez) = the reference array shape; coefficient.
 // ---------------------------------------------------------------------------------------
-template <class A>
-__device__ __forceinline__ typename A::T mur(typename A::T q_inner, typename A::T qn_inner, typename A::T q_face,
-                                             typename A::T c) {
-    return A::add(q_inner, A::mul(c, A::sub(qn_inner, q_face)));
-}
 
 #define PHB_FACE(Q, F, N, C)                                          \
     {                                                                 \
@@ -46,6 +41,8 @@ struct AbcArgs {
     Fld<T> dl;            // COMP state: delta arrays (a face value replaces u_new, so delta = u_new - u is refreshed)
     T clx, ctx, cly0, cty0, cly1, cty1, clz, ctz;
     int i_begin, i_end;   // owned planes the y/z faces cover
+    int z_edges_only;     // the marching kernel applied the z face itself (StepArgs::zface): redo only the columns whose
+                          // inputs the x / y faces have changed since (rows 0, ny-2, ny-1 and planes nx-2, nx-1)
 };
 
 // x = -1 face (only the rank that owns the last planes).  threads over (j, k).
@@ -100,6 +97,7 @@ __global__ void k_abc_z(AbcArgs<typename A::T> p) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = p.i_begin + blockIdx.y * blockDim.y + threadIdx.y;
     if (j >= g.ny || i >= p.i_end) return;
+    if (p.z_edges_only && !(j == 0 || j >= g.ny - 2 || i >= g.nx - 2)) return;
     if (i < g.nx - 1) {
         const long long f = g.idx(i, j, g.nz - 1), n = f - 1;
         PHB_FACE(ux, f, n, p.ctz)

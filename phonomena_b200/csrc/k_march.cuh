@@ -229,7 +229,7 @@ struct MarchMaps {
 };
 
 // ---- the kernel ---------------------------------------------------------------------------------
-template <class A, int R, int NST, bool PUSH, int RW>
+template <class A, int R, int NST, bool PUSH, int RW, bool ZF = false>
 __global__ void __launch_bounds__(R / RW * 32, ((R <= 8 && RW == 1) ? 2 : 1))
 k_step_march(const __grid_constant__ MarchMaps tm, StepArgs<typename A::T> p, MatCls<typename A::T> m, int chunk) {
     using T = typename A::T;
@@ -357,6 +357,8 @@ k_step_march(const __grid_constant__ MarchMaps tm, StepArgs<typename A::T> p, Ma
     const int xo = w * TZ + lane * V;                  // own vector inside an exchange component tile
     const int xS = (w >= 1) ? -TZ : 0, xN = (w <= W - 2) ? TZ : 0;
     const uint32_t pubO = bar_pub + (uint32_t)w * 16;
+    // lane that holds k = nz-2, nz-1 if this block applies the z face itself, else -1
+    const int zlane = (ZF && k0t <= g.nz - 1 && g.nz - 1 < k0t + TZ) ? (g.nz - 1 - k0t) / V : -1;
     const T *const zt = ztab + lane * V;               // this lane's z spacings
     const T *const yt = ytab + 2 * r0;
 
@@ -651,6 +653,24 @@ k_step_march(const __grid_constant__ MarchMaps tm, StepArgs<typename A::T> p, Ma
                     }
                 }
             }
+            // z = -1 absorbing face (base_solver.py:551-554) on the block's own results: ux, uy at k = nz-1 from
+            // k = nz-2, uz at k = nz-2 from k = nz-3.  nz is a multiple of V here (host check), so k = nz-2 and nz-1
+            // are the last two elements of lane zlane; for V = 2 the uz inner point is the previous lane's last element.
+            if constexpr (ZF && !A::COMP) {
+                if (zlane >= 0) {     // block-uniform
+#pragma unroll
+                    for (int q = 0; q < RW; ++q) {
+                        const T un_ = shfl_up1(uzc[q].v[V - 1]), on_ = shfl_up1(oz[q].v[V - 1]);
+                        if (lane == zlane) {
+                            if (n < g.nx - 1) ox[q].v[V - 1] = mur<A>(uxc[q].v[V - 2], ox[q].v[V - 2], uxc[q].v[V - 1], p.zf_ct);
+                            if (j + q < g.ny - 1) oy[q].v[V - 1] = mur<A>(uyc[q].v[V - 2], oy[q].v[V - 2], uyc[q].v[V - 1], p.zf_ct);
+                            const T un = (V >= 3) ? uzc[q].v[V >= 3 ? V - 3 : 0] : un_;
+                            const T on = (V >= 3) ? oz[q].v[V >= 3 ? V - 3 : 0] : on_;
+                            oz[q].v[V - 2] = mur<A>(un, on, uzc[q].v[V - 2], p.zf_cl);
+                        }
+                    }
+                }
+            }
 #pragma unroll
             for (int q = 0; q < RW; ++q) {
                 const int offq = off + q * g.nzp;
@@ -788,8 +808,11 @@ inline int launch_march_cfg(const StepArgs<typename A::T> &p, const MatCls<typen
     if constexpr (!PUSH) {
         if (p.push_lo[0] || p.push_hi[0]) return launch_march_cfg<A, R, NST, RW, true>(p, m, maps, chunks, st);
     }
-    auto kern = k_step_march<A, R, NST, PUSH, RW>;
-    static size_t attr_by_dev[64] = {};   // per template instantiation and device (the attribute is per device)
+    constexpr bool kHasZF = (RW == 2) && !A::COMP;     // instantiations with the fused z face (StepArgs::zface)
+    if (p.zface && !kHasZF) return -3;
+    auto kern = (kHasZF && p.zface) ? k_step_march<A, R, NST, PUSH, RW, kHasZF> : k_step_march<A, R, NST, PUSH, RW, false>;
+    static size_t attr_by_dev2[2][64] = {};   // per template instantiation and device (the attribute is per device)
+    size_t (&attr_by_dev)[64] = attr_by_dev2[p.zface ? 1 : 0];
     int dev = 0;
     cudaGetDevice(&dev);
     size_t &attr_bytes = attr_by_dev[dev & 63];

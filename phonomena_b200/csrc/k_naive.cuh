@@ -17,6 +17,11 @@ struct StepArgs {
     // plane of the left / right neighbour's buffer, mapped through CUDA IPC (NVLink peer stores); null = none
     T *push_lo[3], *push_hi[3];
     int edge_b;           // >= 0: second single plane of an 'edge launch' (planes i_begin and edge_b, one chunk each)
+    // fused z = -1 absorbing face (k_march only, not in COMP mode): the block that owns k = nz-1 applies the Mur
+    // formula to its own results before storing them (the face points and their inner neighbours sit in one
+    // lane); the host then re-applies the face only where the x / y faces change its inputs (k_abc_z, edges only)
+    int zface;
+    T zf_ct, zf_cl;
 };
 
 // u_new for one cell from generic stress evaluations.  Writes only entries the reference's

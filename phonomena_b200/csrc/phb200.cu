@@ -164,6 +164,7 @@ struct phb_ctx {
     // marching kernel: TMA descriptors per [buffer][component], tile plan
     MarchMaps mm[3];           // indexed by the buffer that holds u_cur
     bool maps_ok = false;
+    int zfuse = -1;          // z = -1 face inside the marching kernel: -1 auto, 0 never, 1 whenever possible (PHB_ZFUSE)
     int mR = 16, mNST = 4, mRW = PHB_DEFAULT_RW, mChunks = 0;   // marching kernel: tile rows, u_cur ring depth, rows per warp
     // per-kernel timing of the stencil launches (bench roofline): event pairs on the launch stream
     bool prof = false;
@@ -447,6 +448,8 @@ struct Engine : IEngine {
         p.line_save = (c->w && c->cfg.x0 == 0) ? (const T *)c->line_save : nullptr;
         p.i_begin = ib; p.i_end = ie;
         const bool march = use_march();
+        p.zface = (march && zface_fused()) ? 1 : 0;
+        p.zf_cl = (T)c->abc[6]; p.zf_ct = (T)c->abc[7];
         std::pair<cudaEvent_t, cudaEvent_t> *pe = nullptr;
         if (c->prof) {
             if (c->prof_used == c->prof_ev.size()) {
@@ -474,6 +477,7 @@ struct Engine : IEngine {
                 else if (c->mR == 16 && c->mNST == 3) r = launch_march_cfg<A, 16, 3>(p, m, mp, ch, c->st);
                 else if (c->mR == 8 && c->mNST == 4) r = launch_march_cfg<A, 8, 4>(p, m, mp, ch, c->st);
                 if (r == -2) return fail("no marching-kernel instantiation for R=%d NST=%d", c->mR, c->mNST);
+                if (r == -3) return fail("internal: fused z face requested for a marching-kernel configuration without it");
                 if (r < 0 && (c->cfg.kernel == PHB_KERNEL_MARCH || c->halo == 2))
                     return fail("marching kernel needs more shared memory than the device allows (%d classes)", c->ncls);
                 if (r >= 0) { c->launches += r; return 0; }
@@ -490,6 +494,16 @@ struct Engine : IEngine {
         if (pe) CU(cudaEventRecord(pe->second, c->st));
         CU(cudaGetLastError());
         return 0;
+    }
+    // the marching kernel applies the z = -1 face itself when the face points and their inner neighbours share a
+    // lane: nz a multiple of the vector width, and not in the first lane of a tile (V = 2 reads the lane before)
+    bool zface_fused() const {
+        const int V = VecOf<T>::V, nz = c->cfg.nz;
+        // measured at 512^3: fp32 gains 4 % (the separate strided face kernel costs 48 us per step), fp64 loses as much in
+        // the stencil kernel itself as the face kernel costs -> default on for fp32 only (PHB_ZFUSE=0/1 overrides)
+        const bool want = c->zfuse < 0 ? (sizeof(T) == 4) : (c->zfuse != 0);
+        if (!want || comp() || c->mRW != 2 || nz < 2 * V || nz % V != 0) return false;
+        return ((nz - 1) % (32 * V)) / V >= 1;
     }
     bool use_march() const {
         if (c->cfg.kernel == PHB_KERNEL_NAIVE) return false;
@@ -546,6 +560,7 @@ struct Engine : IEngine {
         a.clx = (T)c->abc[0]; a.ctx = (T)c->abc[1]; a.cly0 = (T)c->abc[2]; a.cty0 = (T)c->abc[3];
         a.cly1 = (T)c->abc[4]; a.cty1 = (T)c->abc[5]; a.clz = (T)c->abc[6]; a.ctz = (T)c->abc[7];
         a.i_begin = ib; a.i_end = ie;
+        a.z_edges_only = 0;
         return a;
     }
     int abc_x() {
@@ -561,6 +576,7 @@ struct Engine : IEngine {
     int abc_yz(int ib, int ie) {
         if (ie <= ib) return 0;
         AbcArgs<T> a = abc_args(ib, ie);
+        a.z_edges_only = (use_march() && zface_fused()) ? 1 : 0;
         {
             dim3 bl = block_for(c->cfg.nz), gr = grid3(c->cfg.nz, ie - ib, 1, bl);
             gr.z = 2;
@@ -827,6 +843,7 @@ int phb_create(const phb_cfg *cfg, phb_ctx **out) {
     if (const char *e = getenv("PHB_MARCH_R")) c->mR = atoi(e);
     if (const char *e = getenv("PHB_MARCH_NST")) c->mNST = atoi(e);
     if (const char *e = getenv("PHB_MARCH_RW")) c->mRW = atoi(e);
+    if (const char *e = getenv("PHB_ZFUSE")) c->zfuse = atoi(e);
     if (c->mRW != 1 && !(c->mRW == 2 && c->mR == 16 && c->mNST == 4)) c->mRW = 1;   // two rows per warp exist for R = 16, NST = 4
     if (const char *e = getenv("PHB_MARCH_CHUNKS")) c->mChunks = atoi(e);
     if (c->mR != 8 && c->mR != 16) return cleanup(fail("PHB_MARCH_R must be 8 or 16"));

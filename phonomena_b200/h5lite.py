@@ -16,7 +16,9 @@ validated by the independent reader below and by structure tests, not by libhdf5
 from __future__ import annotations
 
 import mmap
+import os
 import struct
+import threading
 
 import numpy as np
 
@@ -89,28 +91,43 @@ class H5Writer:
     d = hdf.create_chunked(name, (a, b, c, frames)); hdf.write_frame(d, t, array); hdf.close()"""
 
     def __init__(self, path):
-        self.f = open(path, "wb")
-        self.f.write(b"\0" * 96)            # superblock placeholder
+        # raw descriptor + positional writes: frames of different datasets can be written by several threads at once
+        self.fd = os.open(path, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o644)
+        self._end = 96                      # superblock placeholder
+        self._lock = threading.Lock()
         self.attrs = {}
         self._contig = []                   # (name, shape, addr, nbytes)
         self._chunked = []
         self.closed = False
 
     # -- data ------------------------------------------------------------------------------
+    def _pwrite(self, raw, pos):
+        mv = memoryview(raw).cast("B")
+        while len(mv):
+            n = os.pwrite(self.fd, mv, pos)
+            mv, pos = mv[n:], pos + n
+
     def _append(self, raw):
-        self.f.seek(0, 2)
-        pos = self.f.tell()
-        pad = -pos % 8
-        if pad:
-            self.f.write(b"\0" * pad)
-            pos += pad
-        self.f.write(raw)
+        """Reserve an 8-byte aligned extent at the end of the file and write `raw` there (thread-safe; the
+        write itself runs outside the lock)."""
+        nbytes = memoryview(raw).nbytes
+        with self._lock:
+            pos = self._end + (-self._end % 8)
+            self._end = pos + nbytes
+        self._pwrite(raw, pos)
         return pos
 
     def create_dataset(self, name, data):
         a = np.ascontiguousarray(np.asarray(data, dtype="<f8"))
         addr = self._append(a.tobytes()) if a.size else UNDEF
         self._contig.append((name, a.shape, addr, a.nbytes))
+
+    def settle(self):
+        """Flush what has been written so far to the device (used after the large static datasets)."""
+        try:
+            os.fsync(self.fd)
+        except OSError:
+            pass
 
     def create_chunked(self, name, shape):
         d = _Chunked(name, shape)
@@ -121,9 +138,25 @@ class H5Writer:
         a = np.ascontiguousarray(np.asarray(frame, dtype="<f8"))
         if a.nbytes != d.frame_bytes:
             raise ValueError("frame of %d bytes for dataset %s, expected %d" % (a.nbytes, d.name, d.frame_bytes))
-        if not (0 <= t < d.shape[-1]) or t in d.addr:
-            raise ValueError("bad or repeated frame index %d for %s" % (t, d.name))
+        with self._lock:
+            if not (0 <= t < d.shape[-1]) or t in d.addr:
+                raise ValueError("bad or repeated frame index %d for %s" % (t, d.name))
+            d.addr[t] = None
         d.addr[t] = self._append(a.data)
+
+    def reserve_frame(self, d, t):
+        """Reserve the extent of frame t of chunked dataset d and return its file offset; the caller fills it
+        with pwrite() calls (any number of pieces, from any thread) before close()."""
+        with self._lock:
+            if not (0 <= t < d.shape[-1]) or t in d.addr:
+                raise ValueError("bad or repeated frame index %d for %s" % (t, d.name))
+            pos = self._end + (-self._end % 8)
+            self._end = pos + d.frame_bytes
+            d.addr[t] = pos
+        return pos
+
+    def pwrite(self, raw, pos):
+        self._pwrite(raw, pos)
 
     # -- chunk B-tree (v1, node type 1) --------------------------------------------------------
     def _chunk_btree(self, d):
@@ -141,8 +174,7 @@ class H5Writer:
         level, entries = 0, [(t, t + 1, addr) for t, addr in items]
         while True:
             groups = [entries[i:i + 2 * CHUNK_K] for i in range(0, len(entries), 2 * CHUNK_K)]
-            self.f.seek(0, 2)
-            base = self.f.tell() + (-self.f.tell() % 8)
+            base = self._end + (-self._end % 8)
             addrs = [base + n * node_bytes for n in range(len(groups))]
             out = []
             for n, grp in enumerate(groups):
@@ -205,15 +237,13 @@ class H5Writer:
         msgs = [_msg(0x0011, struct.pack("<QQ", bt_addr, heap_addr))]
         msgs += [_attr_msg(k, v) for k, v in self.attrs.items()]
         root_addr = self._append(_object_header(msgs))
-        self.f.seek(0, 2)
-        eof = self.f.tell()
+        eof = self._end
         sb = SIG + struct.pack("<BBBBBBBB", 0, 0, 0, 0, 0, 8, 8, 0) + struct.pack("<HHI", GROUP_LEAF_K, GROUP_INT_K, 0)
         sb += struct.pack("<QQQQ", 0, UNDEF, eof, UNDEF)
         sb += struct.pack("<QQII", 0, root_addr, 1, 0) + struct.pack("<QQ", bt_addr, heap_addr)
         assert len(sb) == 96
-        self.f.seek(0)
-        self.f.write(sb)
-        self.f.close()
+        self._pwrite(sb, 0)
+        os.close(self.fd)
         self.closed = True
 
     def __enter__(self):

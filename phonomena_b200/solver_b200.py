@@ -75,6 +75,9 @@ class Writer:
     chunk = one frame, so `u[:, :, 0, t]` of the consumers (h5py2gif.py:24,44; analysis.py:59-66)
     works unchanged.  full mode: the reference's full 4-D datasets."""
 
+    WRITE_THREADS = 8      # surface mode: positional writes in flight
+    PIECES = 2             # pieces per recorded component and frame
+
     def __init__(self, path, engine, meta, frames, mode, record_every):
         self.path, self.e, self.mode, self.frames = path, engine, mode, frames
         self.h5 = H5Writer(path)
@@ -92,6 +95,10 @@ class Writer:
             "uy": self.h5.create_chunked("uy", (engine.planes(1), ny - 1, zext or nz, frames)),
             "uz": self.h5.create_chunked("uz", (engine.planes(2), ny, zext or (nz - 1), frames)),
         }
+        # The static datasets (density alone is Nx*Ny*Nz doubles) are pushed out now, in init(), like the reference's
+        # Writer.init (base_solver.py:105-133): otherwise the kernel's dirty-page writeback of them throttles the
+        # frame appends of the stepping loop.
+        self.h5.settle()
         self.written = 0
         self.error = None
         self._stop = threading.Event()
@@ -105,18 +112,33 @@ class Writer:
         self.thread.start()
 
     def _drain(self):
+        # one positional write per recorded component, in parallel (os.pwrite releases the GIL): a single
+        # thread copying 6 MB frames into the page cache is slower than the GPU produces them at 512^3
+        from concurrent.futures import ThreadPoolExecutor
         try:
-            while self.written < self.frames:
-                got = self.e.record_next(timeout_ms=200)
-                if got is None:
-                    if self._stop.is_set():
-                        break
-                    continue
-                _tt, views = got
-                for name, a in views.items():
-                    self.h5.write_frame(self.ds[name], self.written, a.reshape(a.shape + (1,)))
-                self.e.record_release()
-                self.written += 1
+            with ThreadPoolExecutor(max_workers=self.WRITE_THREADS, thread_name_prefix="phb-h5") as pool:
+                while self.written < self.frames:
+                    got = self.e.record_next(timeout_ms=200)
+                    if got is None:
+                        if self._stop.is_set():
+                            break
+                        continue
+                    _tt, views = got
+                    jobs = []
+                    for name, a in views.items():
+                        d = self.ds[name]
+                        mv = memoryview(np.ascontiguousarray(a, dtype="<f8")).cast("B")
+                        if mv.nbytes != d.frame_bytes:
+                            raise ValueError("frame of %d bytes for dataset %s, expected %d" % (mv.nbytes, name, d.frame_bytes))
+                        pos = self.h5.reserve_frame(d, self.written)
+                        piece = -(-mv.nbytes // self.PIECES)
+                        piece += -piece % 4096            # page-aligned pieces
+                        for o in range(0, mv.nbytes, piece):
+                            jobs.append(pool.submit(self.h5.pwrite, mv[o:o + piece], pos + o))
+                    for jb in jobs:
+                        jb.result()
+                    self.e.record_release()
+                    self.written += 1
         except Exception as exc:       # surfaced by Solver.run
             self.error = exc
 
@@ -288,7 +310,9 @@ class Solver:
         finally:
             self.running.clear()
             if self.writer is not None:
+                t_fin = time.time()
                 self.writer.finish()
+                self._finish_seconds = time.time() - t_fin
         if self._nranks > 1 and self.writer is not None and c.get("merge_slabs", True):
             # every slab file is closed (the all-gather doubles as the barrier); rank 0 concatenates along x
             parts = self.allgather(self.writer.path)
@@ -300,7 +324,8 @@ class Solver:
         etime = time.time() - stime
         cells = e.nx * e.ny * e.nz
         self.stats = {"steps": done, "seconds": etime, "gcells_per_s": cells * done / etime / 1e9 if etime > 0 else 0.0,
-                      "launches": e.launch_count - l0, "kernel": e.info()["kernel"]}
+                      "launches": e.launch_count - l0, "kernel": e.info()["kernel"],
+                      "writer_finish_seconds": getattr(self, "_finish_seconds", 0.0)}
         signals.status.emit("Simulation finished in {:.2f}s ({:.2f} Gcell/s).".format(etime, self.stats["gcells_per_s"]))
         signals.progress.emit(100)
 
