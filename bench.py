@@ -288,7 +288,8 @@ def run_e2e(case, n, rank, local, K, dtype, arith, dist):
     s = Solver()
     s.cfg.update({"precision": {"f64": "fp64", "f32": "fp32"}[dtype], "arith": arith, "device": local, "wave": "sin",
                   "wave_args": {"f": 100}, "write_mode": "thread", "record": "surface", "record_every": 1,
-                  "slabs_from_env": n > 1, "chunk_steps": 10})
+                  "slabs_from_env": n > 1, "chunk_steps": 10,
+                  "merge_slabs": False})      # N > 1: one slab file per rank (concatenating them is post-processing)
     # output file: tmpfs when the box has one with room (the run measures the solver and its copies, not the
     # scratch disk of the box), else the temp directory; reported in e2e["file_dir"]
     out_dir = tempfile.gettempdir()
