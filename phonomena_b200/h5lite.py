@@ -129,6 +129,14 @@ class H5Writer:
         except OSError:
             pass
 
+    def preallocate(self, nbytes):
+        """Reserve file space for `nbytes` more data now (posix_fallocate): on tmpfs / page cache the pages are then
+        allocated outside the stepping loop and the frame writes are plain copies.  Best effort."""
+        try:
+            os.posix_fallocate(self.fd, self._end, int(nbytes))
+        except (OSError, AttributeError):
+            pass
+
     def create_chunked(self, name, shape):
         d = _Chunked(name, shape)
         self._chunked.append(d)
@@ -243,6 +251,10 @@ class H5Writer:
         sb += struct.pack("<QQII", 0, root_addr, 1, 0) + struct.pack("<QQ", bt_addr, heap_addr)
         assert len(sb) == 96
         self._pwrite(sb, 0)
+        try:
+            os.ftruncate(self.fd, eof)          # drop preallocated space that was not used
+        except OSError:
+            pass
         os.close(self.fd)
         self.closed = True
 

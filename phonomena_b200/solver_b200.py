@@ -98,8 +98,11 @@ class Writer:
         # The static datasets (density alone is Nx*Ny*Nz doubles) are pushed out now, in init(), like the reference's
         # Writer.init (base_solver.py:105-133): otherwise the kernel's dirty-page writeback of them throttles the
         # frame appends of the stepping loop.
+        if mode == "surface":
+            self.h5.preallocate(frames * sum(d.frame_bytes + 8 for d in self.ds.values()))
         self.h5.settle()
         self.written = 0
+        self.wait_seconds = self.write_seconds = 0.0     # writer thread: waiting for frames / writing them
         self.error = None
         self._stop = threading.Event()
         self.thread = None
@@ -118,7 +121,10 @@ class Writer:
         try:
             with ThreadPoolExecutor(max_workers=self.WRITE_THREADS, thread_name_prefix="phb-h5") as pool:
                 while self.written < self.frames:
+                    t0 = time.perf_counter()
                     got = self.e.record_next(timeout_ms=200)
+                    t1 = time.perf_counter()
+                    self.wait_seconds += t1 - t0
                     if got is None:
                         if self._stop.is_set():
                             break
@@ -139,6 +145,7 @@ class Writer:
                         jb.result()
                     self.e.record_release()
                     self.written += 1
+                    self.write_seconds += time.perf_counter() - t1
         except Exception as exc:       # surfaced by Solver.run
             self.error = exc
 
@@ -307,6 +314,7 @@ class Solver:
                     progress = min(99, int((done / self.t) * 100))
                     signals.progress.emit(progress)
             e.sync()
+            self._loop_seconds = time.time() - stime
         finally:
             self.running.clear()
             if self.writer is not None:
@@ -325,7 +333,10 @@ class Solver:
         cells = e.nx * e.ny * e.nz
         self.stats = {"steps": done, "seconds": etime, "gcells_per_s": cells * done / etime / 1e9 if etime > 0 else 0.0,
                       "launches": e.launch_count - l0, "kernel": e.info()["kernel"],
-                      "writer_finish_seconds": getattr(self, "_finish_seconds", 0.0)}
+                      "loop_seconds": getattr(self, "_loop_seconds", 0.0),
+                      "writer_finish_seconds": getattr(self, "_finish_seconds", 0.0),
+                      "writer_wait_seconds": self.writer.wait_seconds if self.writer is not None else 0.0,
+                      "writer_write_seconds": self.writer.write_seconds if self.writer is not None else 0.0}
         signals.status.emit("Simulation finished in {:.2f}s ({:.2f} Gcell/s).".format(etime, self.stats["gcells_per_s"]))
         signals.progress.emit(100)
 
