@@ -10,13 +10,18 @@ namespace phb {
 // (base_solver.py:251).  The overwritten line is saved first: the reference's u_new keeps
 // the pre-source value there (App. B #9) and the step kernel re-emits it.
 // ---------------------------------------------------------------------------------------
+// One block; the sample index lives in device memory and is advanced here, after every thread has read it, so
+// the launch has no per-step argument and a captured CUDA graph of the step can be replayed (phb200.cu step()).
 template <class T>
-__global__ void k_source(Geo<T> g, T *uz_cur, T *line_save, const double *w, long long tt) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= g.ny) return;
-    const long long c = g.idx(0, j, 0);
-    line_save[j] = uz_cur[c];
-    uz_cur[c] = (T)w[tt];
+__global__ void k_source(Geo<T> g, T *uz_cur, T *line_save, const double *w, long long *idx) {
+    const T v = (T)w[*idx];
+    for (int j = threadIdx.x; j < g.ny; j += blockDim.x) {
+        const long long c = g.idx(0, j, 0);
+        line_save[j] = uz_cur[c];
+        uz_cur[c] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) ++*idx;
 }
 
 // ---------------------------------------------------------------------------------------

@@ -134,8 +134,15 @@ struct phb_ctx {
     void *tab = nullptr;       // class table, ncls x CLS_W
     int ncls = 0;
     void *line_save = nullptr;
-    double *w = nullptr;       // source samples for steps w_base .. w_base + nw - 1
-    long long nw = 0, w_base = 0;
+    double *w = nullptr;       // source samples for steps w_base .. w_base + nw - 1 (capacity w_cap, pointer kept while it fits)
+    long long nw = 0, w_base = 0, w_cap = 0;
+    long long *src_idx = nullptr;   // device: index into w of the next step's sample (k_source advances it)
+    // single-GPU steps replayed as CUDA graphs (one per buffer rotation phase): a step is 5 short launches, and on
+    // small grids the host's launch rate, not the GPU, sets the pace
+    cudaGraphExec_t gexec[3] = {};
+    int gnodes[3] = {0, 0, 0};
+    int graph_mode = 1;             // PHB_GRAPH=0 disables
+    long long plain_steps = 0;      // steps launched kernel by kernel since the last graph invalidation
     double abc[8] = {};
     bool have_abc = false;
     long long tt = 0;
@@ -178,6 +185,14 @@ struct phb_ctx {
     IEngine *eng = nullptr;
     std::mutex mu;
 };
+
+static void graph_invalidate(phb_ctx *c) {
+    for (int q = 0; q < 3; ++q) {
+        if (c->gexec[q]) cudaGraphExecDestroy(c->gexec[q]);
+        c->gexec[q] = nullptr;
+    }
+    c->plain_steps = 0;
+}
 
 static int prof_collect(phb_ctx *c) {
     for (size_t q = 0; q < c->prof_used; ++q) {
@@ -507,6 +522,10 @@ struct Engine : IEngine {
     }
     bool use_march() const {
         if (c->cfg.kernel == PHB_KERNEL_NAIVE) return false;
+        // kernel = auto on a small slab: the x-march is a serial chain per (y, z) tile, and a grid of a few thousand
+        // cells has too few tiles to fill the SMs -- one thread per cell is faster there (measured: 32^3 25 vs 33 us per
+        // step, equal at 64^3, 2x slower at 96^3; EXACT arithmetic 8x faster on the 31x21x6 default.json grid)
+        if (c->cfg.kernel == PHB_KERNEL_AUTO && (long long)c->cfg.nxl * c->cfg.ny * c->cfg.nz < 200000) return false;
         return c->maps_ok && march_fits();
     }
     // x-chunks per launch: fill whole waves of (148 SMs x resident blocks) with the (y,z) tiles
@@ -634,13 +653,52 @@ struct Engine : IEngine {
     }
 
     int step() override {
+        if (c->w && c->cfg.x0 == 0 && c->tt - c->w_base >= c->nw)
+            return fail("source table covers steps %lld..%lld, step %lld requested", c->w_base, c->w_base + c->nw - 1, c->tt);
+        // single GPU: replay the step as a CUDA graph (captured per rotation phase after a few plain steps)
+        const bool graphable = c->graph_mode && c->nranks == 1 && !c->prof;
+        if (graphable && c->plain_steps >= 3) {
+            const int ph = c->cur;
+            if (!c->gexec[ph]) {
+                cudaGraph_t gr = nullptr;
+                const long long l0 = c->launches.load();
+                CU(cudaStreamBeginCapture(c->st, cudaStreamCaptureModeThreadLocal));
+                const int rc = launch_step();
+                const cudaError_t ce = cudaStreamEndCapture(c->st, &gr);
+                c->gnodes[ph] = (int)(c->launches.load() - l0);
+                c->launches -= c->gnodes[ph];
+                if (rc != 0 || ce != cudaSuccess || !gr) {
+                    if (gr) cudaGraphDestroy(gr);
+                    cudaGetLastError();
+                    c->graph_mode = 0;                 // capture refused: keep launching kernel by kernel
+                    if (rc != 0) return rc;
+                } else {
+                    const cudaError_t ie = cudaGraphInstantiate(&c->gexec[ph], gr, 0);
+                    cudaGraphDestroy(gr);
+                    if (ie != cudaSuccess) { cudaGetLastError(); c->gexec[ph] = nullptr; c->graph_mode = 0; }
+                }
+            }
+            if (c->gexec[ph]) {
+                CU(cudaGraphLaunch(c->gexec[ph], c->st));
+                c->launches += c->gnodes[ph];
+                c->cur = b_new();
+                c->tt++;
+                return 0;
+            }
+        }
+        OK(launch_step());
+        c->plain_steps++;
+        c->cur = b_new();   // rotate: old <- cur, cur <- new
+        c->tt++;
+        return 0;
+    }
+
+    // the launches of one time step on c->st (does not advance tt / rotate)
+    int launch_step() {
         const int x0 = c->cfg.x0, xe = c->cfg.x0 + c->cfg.nxl;
         const bool last = (xe == c->cfg.nx);
         if (c->w && x0 == 0) {
-            if (c->tt - c->w_base >= c->nw)
-                return fail("source table covers steps %lld..%lld, step %lld requested", c->w_base, c->w_base + c->nw - 1, c->tt);
-            k_source<T><<<(c->cfg.ny + 127) / 128, 128, 0, c->st>>>(geo(), (T *)c->buf[b_cur()][2], (T *)c->line_save,
-                                                                   c->w, c->tt - c->w_base);
+            k_source<T><<<1, 256, 0, c->st>>>(geo(), (T *)c->buf[b_cur()][2], (T *)c->line_save, c->w, c->src_idx);
             c->launches++;
         }
         if (c->halo == 2 && c->nranks > 1) {
@@ -658,8 +716,6 @@ struct Engine : IEngine {
             if (hasR) OK(wait_flag(c->flags + 1, stepno));
             if (last) OK(abc_x());
             OK(abc_yz(x0 - (hasL ? 1 : 0), xe + (hasR ? 1 : 0)));
-            c->cur = b_new();
-            c->tt++;
             return 0;
         }
         static const int fake_edges = getenv("PHB_DEBUG_FAKE_EDGES") ? atoi(getenv("PHB_DEBUG_FAKE_EDGES")) : 0;   // timing aid
@@ -689,8 +745,6 @@ struct Engine : IEngine {
             if (last) OK(abc_x());
             OK(abc_yz(x0, xe));
         }
-        c->cur = b_new();   // rotate: old <- cur, cur <- new
-        c->tt++;
         return 0;
     }
 };
@@ -844,6 +898,7 @@ int phb_create(const phb_cfg *cfg, phb_ctx **out) {
     if (const char *e = getenv("PHB_MARCH_NST")) c->mNST = atoi(e);
     if (const char *e = getenv("PHB_MARCH_RW")) c->mRW = atoi(e);
     if (const char *e = getenv("PHB_ZFUSE")) c->zfuse = atoi(e);
+    if (const char *e = getenv("PHB_GRAPH")) c->graph_mode = atoi(e) != 0;
     if (c->mRW != 1 && !(c->mRW == 2 && c->mR == 16 && c->mNST == 4)) c->mRW = 1;   // two rows per warp exist for R = 16, NST = 4
     if (const char *e = getenv("PHB_MARCH_CHUNKS")) c->mChunks = atoi(e);
     if (c->mR != 8 && c->mR != 16) return cleanup(fail("PHB_MARCH_R must be 8 or 16"));
@@ -885,7 +940,9 @@ int phb_destroy(phb_ctx *c) {
     for (int b = 0; b < 3; ++b) cudaFree(c->buf[b][0]);
     for (int a = 0; a < 6; ++a) cudaFree(c->sp[a]);
     cudaFree(c->tab); cudaFree(c->ids); cudaFree(c->code); cudaFree(c->line_save);
+    graph_invalidate(c);
     if (c->w) cudaFree(c->w);
+    cudaFree(c->src_idx);
     if (c->ring) cudaFreeHost(c->ring);
     for (auto &ev : c->slot_ev) cudaEventDestroy(ev);
     for (auto &ev : c->stage_ev) cudaEventDestroy(ev);
@@ -912,12 +969,14 @@ int phb_destroy(phb_ctx *c) {
 int phb_set_spacing(phb_ctx *c, const double *fdx, const double *fdy, const double *fdz, const double *sdx,
                     const double *sdy, const double *sdz) {
     ENTER(c);
+    graph_invalidate(c);
     if (!fdx || !fdy || !fdz || !sdx || !sdy || !sdz) return fail("null spacing array");
     return c->eng->set_spacing(fdx, fdy, fdz, sdx, sdy, sdz);
 }
 
 int phb_set_material_table(phb_ctx *c, int32_t nmat, const double *c12, const double *rho) {
     ENTER(c);
+    graph_invalidate(c);
     if (nmat < 1 || nmat > MAX_MAT) return fail("nmat must be 1..%d (got %d)", (int)MAX_MAT, nmat);
     for (int m = 0; m < nmat; ++m)
         if (!(rho[m] > 0)) return fail("density of material %d is not positive", m);
@@ -934,6 +993,7 @@ static int ids_planes(const phb_ctx *c, int *ib, int *ie) {
 
 int phb_set_material_ids(phb_ctx *c, const uint8_t *ids, int64_t nplanes) {
     ENTER(c);
+    graph_invalidate(c);
     int ib, ie;
     const int np = ids_planes(c, &ib, &ie);
     if (nplanes != np) return fail("expected %d id planes [%d, %d), got %lld", np, ib, ie, (long long)nplanes);
@@ -985,6 +1045,7 @@ int phb_set_material_dense(phb_ctx *c, const double *C, const double *P, int64_t
 
 int phb_gen_material_ids(phb_ctx *c, const float *tg, int32_t n, const double *x, const double *y, const double *z) {
     ENTER(c);
+    graph_invalidate(c);
     if (n < 0 || (n && !tg) || !x || !y || !z) return fail("bad arguments");
     const int nx = c->cfg.nx, ny = c->cfg.ny, nz = c->cfg.nz;
     int ib, ie;
@@ -1058,17 +1119,32 @@ int phb_get_material_ids(phb_ctx *c, uint8_t *ids) {
 
 int phb_set_abc(phb_ctx *c, const double coef[8]) {
     ENTER(c);
+    graph_invalidate(c);
     return c->eng->set_abc(coef);
 }
 
 int phb_set_source_table(phb_ctx *c, const double *w, int64_t n) {
     ENTER(c);
-    // the previous table may still be read by enqueued steps: stream-ordered free
-    if (c->w) { CU(cudaFreeAsync(c->w, c->st)); c->w = nullptr; c->nw = 0; }
-    if (!w || n <= 0) return 0;
-    CU(cudaMallocAsync((void **)&c->w, (size_t)n * sizeof(double), c->st));
-    CU(cudaMemcpyAsync(c->w, w, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->st));
-    CU(cudaStreamSynchronize(c->st));
+    // The previous table may still be read by enqueued steps: everything here is ordered on the launch stream.
+    // The buffer (and the captured graphs that hold its address) is kept while the new table fits.
+    if (!w || n <= 0) {
+        if (c->w) { CU(cudaFreeAsync(c->w, c->st)); c->w = nullptr; graph_invalidate(c); }
+        c->nw = c->w_cap = 0;
+        return 0;
+    }
+    if (!c->src_idx) {
+        CU(cudaMalloc((void **)&c->src_idx, sizeof(long long)));
+        graph_invalidate(c);
+    }
+    if (n > c->w_cap) {
+        if (c->w) CU(cudaFreeAsync(c->w, c->st));
+        c->w = nullptr;
+        c->w_cap = std::max<long long>(n, 1024);
+        CU(cudaMallocAsync((void **)&c->w, (size_t)c->w_cap * sizeof(double), c->st));
+        graph_invalidate(c);
+    }
+    CU(cudaMemcpyAsync(c->w, w, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->st));   // pageable source: staged before return
+    CU(cudaMemsetAsync(c->src_idx, 0, sizeof(long long), c->st));
     c->nw = n;
     c->w_base = c->tt;
     return 0;
@@ -1148,6 +1224,7 @@ int phb_info(phb_ctx *c, char *name, int32_t len, int64_t *bytes) {
 
 int phb_profile(phb_ctx *c, int32_t enable, double *kernel_ms, int64_t *kernel_launches) {
     ENTER(c);
+    graph_invalidate(c);
     OK(prof_collect(c));
     if (kernel_ms) *kernel_ms = c->prof_ms;
     if (kernel_launches) *kernel_launches = c->prof_n;
@@ -1169,6 +1246,7 @@ int phb_comm_unique_id(char id[128]) {
 }
 int phb_comm_init(phb_ctx *c, const char id[128], int32_t rank, int32_t nranks) {
     ENTER(c);
+    graph_invalidate(c);
     if (nranks < 1 || rank < 0 || rank >= nranks) return fail("bad rank %d of %d", rank, nranks);
     c->rank = rank; c->nranks = nranks;
     if (nranks == 1) return 0;
@@ -1216,6 +1294,7 @@ int phb_p2p_export(phb_ctx *c, char handles[256], int32_t *nxl) {
 int phb_p2p_import(phb_ctx *c, int32_t rank, int32_t nranks, const char *left, int32_t left_nxl, const char *right,
                    int32_t right_nxl) {
     ENTER(c);
+    graph_invalidate(c);
     if (nranks < 1 || rank < 0 || rank >= nranks) return fail("bad rank %d of %d", rank, nranks);
     if (!c->flags) return fail("call phb_p2p_export first");
     c->rank = rank; c->nranks = nranks;

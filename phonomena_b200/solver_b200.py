@@ -77,6 +77,7 @@ class Writer:
 
     WRITE_THREADS = 8      # surface mode: positional writes in flight
     PIECES = 2             # pieces per recorded component and frame
+    PARALLEL_MIN_BYTES = 1 << 19
 
     def __init__(self, path, engine, meta, frames, mode, record_every):
         self.path, self.e, self.mode, self.frames = path, engine, mode, frames
@@ -137,6 +138,9 @@ class Writer:
                         if mv.nbytes != d.frame_bytes:
                             raise ValueError("frame of %d bytes for dataset %s, expected %d" % (mv.nbytes, name, d.frame_bytes))
                         pos = self.h5.reserve_frame(d, self.written)
+                        if mv.nbytes < self.PARALLEL_MIN_BYTES:       # small grids: one write, no hand-off
+                            self.h5.pwrite(mv, pos)
+                            continue
                         piece = -(-mv.nbytes // self.PIECES)
                         piece += -piece % 4096            # page-aligned pieces
                         for o in range(0, mv.nbytes, piece):

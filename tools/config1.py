@@ -13,7 +13,7 @@ for mode, cfg in (("fp64 exact, surface HDF5", {"arith": "exact", "record": "sur
                   ("fp64 fast, surface HDF5", {"arith": "fast", "record": "surface", "write_mode": "thread"}),
                   ("fp64 fast, full-field HDF5 (reference schema)", {"arith": "fast", "record": "full", "write_mode": "thread"}),
                   ("fp64 fast, no output", {"arith": "fast", "write_mode": "off"})):
-    s = Solver(); s.cfg.update({"wave": "sin", "wave_args": {"f": 100}, "chunk_steps": 250}); s.cfg.update(cfg)
+    s = Solver(); s.cfg.update({"wave": "sin", "wave_args": {"f": 100}, "chunk_steps": 250, "kernel": os.environ.get("CFG1_KERNEL", "auto")}); s.cfg.update(cfg)
     s.file = os.path.join(tempfile.gettempdir(), "cfg1.h5")
     g, m = fake_from_golden(d)
     s.init(g, m, 1000); s.run()          # warm
