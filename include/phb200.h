@@ -44,7 +44,9 @@ enum { PHB_FAST = 0, PHB_EXACT = 1, PHB_COMP = 2 };
  *             delta += dt^2/rho * div T;  u_new = u + delta.  Same step algebraically; keeps fp32 within
  *             1e-5 of the reference over >= 10^4 steps (plain fp32 drifts to 6e-5), at 12 instead of 9
  *             field words of traffic per cell. */
-/* stencil kernel selection */
+/* stencil kernel selection: MARCH = the TMA-fed x-marching kernel (k_march.cuh), NAIVE = one thread per cell
+ * (k_naive.cuh, the on-device specification); AUTO = MARCH except on slabs below 200 000 cells (too few tiles
+ * for the serial x-march) and when the stencil-class table does not fit beside the shared-memory rings */
 enum { PHB_KERNEL_AUTO = 0, PHB_KERNEL_NAIVE = 1, PHB_KERNEL_MARCH = 2 };
 /* which displacement buffer */
 enum { PHB_CUR = 0, PHB_OLD = 1 };
@@ -110,7 +112,9 @@ int phb_set_abc(phb_ctx *ctx, const double coef[8]);
 
 /* replaces: wave_fn(tt) (base_solver.py:251,294-312): the source samples of the NEXT n steps
  * (w[0] belongs to the step phb_steps_done() reports now), evaluated by the host with the
- * reference's own expression.  May be called between phb_run calls to stream the samples. */
+ * reference's own expression.  May be called between phb_run calls to stream the samples: the copy is ordered
+ * on the library's launch stream behind the steps already enqueued (no synchronisation) and the caller's
+ * array may be reused as soon as the call returns. */
 int phb_set_source_table(phb_ctx *ctx, const double *w, int64_t n);
 
 /* field transfer (tests, restart, full-field output); which = PHB_CUR | PHB_OLD.
