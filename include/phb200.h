@@ -51,7 +51,8 @@ enum { PHB_KERNEL_AUTO = 0, PHB_KERNEL_NAIVE = 1, PHB_KERNEL_MARCH = 2 };
 /* which displacement buffer */
 enum { PHB_CUR = 0, PHB_OLD = 1 };
 /* surface components to record (bit mask) */
-enum { PHB_REC_UX = 1, PHB_REC_UY = 2, PHB_REC_UZ = 4 };
+enum { PHB_REC_UX = 1, PHB_REC_UY = 2, PHB_REC_UZ = 4,
+       PHB_REC_FULL = 8 };   /* frames hold the whole arrays (reference shapes, z fastest) instead of their k = 0 planes */
 
 typedef struct phb_cfg {
     int32_t nx, ny, nz;      /* global grid points: grid.x.size, grid.y.size, grid.z.size        */

@@ -18,7 +18,7 @@ F32, F64 = 0, 1
 FAST, EXACT, COMP = 0, 1, 2
 KERNEL_AUTO, KERNEL_NAIVE, KERNEL_MARCH = 0, 1, 2
 CUR, OLD = 0, 1
-REC_UX, REC_UY, REC_UZ = 1, 2, 4
+REC_UX, REC_UY, REC_UZ, REC_FULL = 1, 2, 4, 8
 
 # every symbol include/phb200.h declares (tests check the .so exports all of them)
 SYMBOLS = (
@@ -339,12 +339,13 @@ class Engine:
     def frame_layout(self):
         """[(name, shape)] of the recorded components inside one frame."""
         out = []
+        full = bool(self.record_mask & REC_FULL)      # whole arrays instead of their k = 0 planes
         if self.record_mask & REC_UX:
-            out.append(("ux", (self.planes(0), self.ny)))
+            out.append(("ux", (self.planes(0), self.ny) + ((self.nz,) if full else ())))
         if self.record_mask & REC_UY:
-            out.append(("uy", (self.nxl, self.ny - 1)))
+            out.append(("uy", (self.nxl, self.ny - 1) + ((self.nz,) if full else ())))
         if self.record_mask & REC_UZ:
-            out.append(("uz", (self.nxl, self.ny)))
+            out.append(("uz", (self.nxl, self.ny) + ((self.nz - 1,) if full else ())))
         return out
 
     def record_next(self, timeout_ms=1000):
@@ -359,7 +360,7 @@ class Engine:
         flat = np.ctypeslib.as_array(p, shape=(self.frame_doubles(),))
         views, off = {}, 0
         for name, shp in self.frame_layout():
-            n = shp[0] * shp[1]
+            n = int(np.prod(shp))
             views[name] = flat[off:off + n].reshape(shp)
             off += n
         return tt.value, views

@@ -759,15 +759,35 @@ static int record_frame(phb_ctx *c) {
     const int s = (int)(f % c->slots);
     double *slot = c->ring_dev + (long long)s * c->frame_doubles;
     const int npx = std::max(0, std::min(c->cfg.x0 + c->cfg.nxl, c->cfg.nx - 1) - c->cfg.x0), npyz = c->cfg.nxl;
-    dim3 bl(128, 1, 1), gr((c->cfg.ny + 127) / 128, c->cfg.nxl, 1);
-    if (c->cfg.dtype == PHB_F64) {
-        auto *e = static_cast<Engine<double> *>(c->eng);
-        k_record<double><<<gr, bl, 0, c->st>>>(e->geo(), e->fld(c->cur), c->cfg.record_mask, slot, npx, npyz);
+    if (c->cfg.record_mask & PHB_REC_FULL) {
+        // whole arrays in the reference's shapes, one coalesced gather per component (the kernel get_fields uses)
+        const int ny = c->cfg.ny, nz = c->cfg.nz;
+        const int np[3] = {npx, npyz, npyz}, ey[3] = {ny, ny - 1, ny}, ez[3] = {nz, nz, nz - 1};
+        double *o = slot;
+        for (int comp = 0; comp < 3; ++comp) {
+            if (!(c->cfg.record_mask & (1 << comp))) continue;
+            const long long cnt = (long long)np[comp] * ey[comp] * ez[comp];
+            if (cnt > 0) {
+                dim3 bl = block_for(ez[comp]), gr = grid3(ez[comp], ey[comp], np[comp], bl);
+                if (c->cfg.dtype == PHB_F64)
+                    k_gather<double><<<gr, bl, 0, c->st>>>((const double *)c->buf[c->cur][comp], o, np[comp], ey[comp], ez[comp], 1, ny, c->nzp);
+                else
+                    k_gather<float><<<gr, bl, 0, c->st>>>((const float *)c->buf[c->cur][comp], o, np[comp], ey[comp], ez[comp], 1, ny, c->nzp);
+                c->launches++;
+            }
+            o += cnt;
+        }
     } else {
-        auto *e = static_cast<Engine<float> *>(c->eng);
-        k_record<float><<<gr, bl, 0, c->st>>>(e->geo(), e->fld(c->cur), c->cfg.record_mask, slot, npx, npyz);
+        dim3 bl(128, 1, 1), gr((c->cfg.ny + 127) / 128, c->cfg.nxl, 1);
+        if (c->cfg.dtype == PHB_F64) {
+            auto *e = static_cast<Engine<double> *>(c->eng);
+            k_record<double><<<gr, bl, 0, c->st>>>(e->geo(), e->fld(c->cur), c->cfg.record_mask, slot, npx, npyz);
+        } else {
+            auto *e = static_cast<Engine<float> *>(c->eng);
+            k_record<float><<<gr, bl, 0, c->st>>>(e->geo(), e->fld(c->cur), c->cfg.record_mask, slot, npx, npyz);
+        }
+        c->launches++;
     }
-    c->launches++;
     CU(cudaGetLastError());
     CU(cudaEventRecord(c->stage_ev[s], c->st));
     CU(cudaStreamWaitEvent(c->rst, c->stage_ev[s], 0));
@@ -909,9 +929,11 @@ int phb_create(const phb_cfg *cfg, phb_ctx **out) {
     if (cfg->record_mask) {
         const int npx = std::max(0, std::min(cfg->x0 + cfg->nxl, cfg->nx - 1) - cfg->x0);
         long long fd = 0;
-        if (cfg->record_mask & PHB_REC_UX) fd += (long long)npx * cfg->ny;
-        if (cfg->record_mask & PHB_REC_UY) fd += (long long)cfg->nxl * (cfg->ny - 1);
-        if (cfg->record_mask & PHB_REC_UZ) fd += (long long)cfg->nxl * cfg->ny;
+        const bool full = (cfg->record_mask & PHB_REC_FULL) != 0;      // whole arrays: Grid.freezeData (grid.py:68-77)
+        if (cfg->record_mask & PHB_REC_UX) fd += (long long)npx * cfg->ny * (full ? cfg->nz : 1);
+        if (cfg->record_mask & PHB_REC_UY) fd += (long long)cfg->nxl * (cfg->ny - 1) * (full ? cfg->nz : 1);
+        if (cfg->record_mask & PHB_REC_UZ) fd += (long long)cfg->nxl * cfg->ny * (full ? cfg->nz - 1 : 1);
+        if (fd <= 0) return cleanup(fail("record_mask %d selects no component", cfg->record_mask));
         c->frame_doubles = fd;
         c->slots = cfg->ring_slots > 0 ? cfg->ring_slots : 16;
         if (cudaHostAlloc((void **)&c->ring, (size_t)c->slots * fd * sizeof(double), cudaHostAllocDefault) != cudaSuccess)

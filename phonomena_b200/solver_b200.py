@@ -78,9 +78,11 @@ class Writer:
     WRITE_THREADS = 8      # surface mode: positional writes in flight
     PIECES = 2             # pieces per recorded component and frame
     PARALLEL_MIN_BYTES = 1 << 19
+    PREALLOCATE_MAX_BYTES = 2 << 30
 
-    def __init__(self, path, engine, meta, frames, mode, record_every):
+    def __init__(self, path, engine, meta, frames, mode, record_every, ring=True):
         self.path, self.e, self.mode, self.frames = path, engine, mode, frames
+        self.ring = ring or mode == "surface"      # frames arrive through the device / pinned ring (else: put_full)
         self.h5 = H5Writer(path)
         self.h5.attrs.update(meta["attrs"])
         self.h5.attrs["record_every"] = int(record_every)
@@ -99,8 +101,9 @@ class Writer:
         # The static datasets (density alone is Nx*Ny*Nz doubles) are pushed out now, in init(), like the reference's
         # Writer.init (base_solver.py:105-133): otherwise the kernel's dirty-page writeback of them throttles the
         # frame appends of the stepping loop.
-        if mode == "surface":
-            self.h5.preallocate(frames * sum(d.frame_bytes + 8 for d in self.ds.values()))
+        total = frames * sum(d.frame_bytes + 8 for d in self.ds.values())
+        if self.ring and total <= self.PREALLOCATE_MAX_BYTES:
+            self.h5.preallocate(total)
         self.h5.settle()
         self.written = 0
         self.wait_seconds = self.write_seconds = 0.0     # writer thread: waiting for frames / writing them
@@ -108,9 +111,9 @@ class Writer:
         self._stop = threading.Event()
         self.thread = None
 
-    # surface mode: consumer thread of the pinned ring
+    # consumer thread of the pinned ring (surface frames, or whole arrays when they fit a ring)
     def start(self):
-        if self.mode != "surface":
+        if not self.ring:
             return
         self.thread = threading.Thread(target=self._drain, name="phb-writer", daemon=True)
         self.thread.start()
@@ -134,7 +137,7 @@ class Writer:
                     jobs = []
                     for name, a in views.items():
                         d = self.ds[name]
-                        mv = memoryview(np.ascontiguousarray(a, dtype="<f8")).cast("B")
+                        mv = memoryview(np.ascontiguousarray(a, dtype="<f8").reshape(-1)).cast("B")
                         if mv.nbytes != d.frame_bytes:
                             raise ValueError("frame of %d bytes for dataset %s, expected %d" % (mv.nbytes, name, d.frame_bytes))
                         pos = self.h5.reserve_frame(d, self.written)
@@ -172,6 +175,8 @@ class Writer:
 
 
 class Solver:
+    FULL_RING_MAX_FRAME_BYTES = 64 << 20     # record = "full": frames up to this size stream through the recorder ring
+
     def __init__(self):
         self.name = "b200"
         self.description = ("<p>FDTD time stepping on an NVIDIA B200 (sm_100a): fused stress + displacement "
@@ -221,12 +226,23 @@ class Solver:
         targets = _targets_array(getattr(mg, "targets", None))
 
         rec_mode = c["record"] if c.get("write_mode", "off") != "off" else "off"
-        rec_mask = (_lib.REC_UX | _lib.REC_UY | _lib.REC_UZ) if rec_mode == "surface" else 0
         x0, nxl, rank, nranks = slab_from_env(x.size) if c.get("slabs_from_env") else (0, x.size, 0, 1)
+        rec_mask, ring_slots = 0, 32
+        if rec_mode == "surface":
+            rec_mask = _lib.REC_UX | _lib.REC_UY | _lib.REC_UZ
+        elif rec_mode == "full":
+            # whole arrays every recorded step (the reference's Writer, base_solver.py:97-100,135-160): when a frame is
+            # small enough they go through the same device ring -> pinned ring -> writer thread as the surface planes,
+            # so the stepping loop never waits for a read-back; big grids keep the synchronous get_fields path
+            fbytes = 8 * nxl * y.size * z.size * 3
+            if fbytes <= self.FULL_RING_MAX_FRAME_BYTES:
+                rec_mask = _lib.REC_UX | _lib.REC_UY | _lib.REC_UZ | _lib.REC_FULL
+                ring_slots = int(max(4, min(32, (256 << 20) // max(1, fbytes))))
+        self._full_ring = bool(rec_mask & _lib.REC_FULL)
         e = _lib.Engine(x.size, y.size, z.size, dt, d2=dt ** 2,
                         dtype={"fp64": "f64", "fp32": "f32"}[c["precision"]], arith=c["arith"],
                         device=int(c["device"]), x0=x0, nxl=nxl, kernel=c.get("kernel", "auto"),
-                        record_mask=rec_mask, record_every=int(c["record_every"]), ring_slots=32)
+                        record_mask=rec_mask, record_every=int(c["record_every"]), ring_slots=ring_slots)
         self.engine = e
         if nranks > 1:
             # one process per GPU: fused NVLink halo push (CUDA IPC handles all-gathered over any host channel,
@@ -275,7 +291,7 @@ class Solver:
             if rec_mode == "full" and P.size <= 1 << 22:      # the reference's `elasticity` is 288 B/cell
                 meta["elasticity"] = np.array(C_out, np.float64) if dense else np.where((ids == 1)[..., None, None], sec["c"], prim["c"])
             path = self.file if nranks == 1 else "%s.rank%d" % (self.file, rank)      # one file per slab
-            self.writer = Writer(path, e, meta, frames, rec_mode, int(c["record_every"]))
+            self.writer = Writer(path, e, meta, frames, rec_mode, int(c["record_every"]), ring=self._full_ring)
             self.writer.start()
         self._rec_mode = rec_mode
 
@@ -301,16 +317,17 @@ class Solver:
                     self.logger.warning("Simulation cancelled.")
                     break
                 n = min(chunk, self.t - done)
-                if self._rec_mode == "full":
+                if self._rec_mode == "full" and not self._full_ring:
                     n = min(n, every - (done % every))
                 # the source samples of this chunk: evaluated on the host with the reference's
                 # expression and copied to the device inside the loop (base_solver.py:251)
                 e.set_source_table(hm.source_table(self._wave, n, self.dt, self._wave_args, start=done))
                 e.run(n)
                 done += n
-                if self._rec_mode == "full" and done % every == 0:
-                    self.writer.put_full(e.get_fields())
-                elif self._rec_mode != "surface":
+                if self._rec_mode == "full" and not self._full_ring:
+                    if done % every == 0:
+                        self.writer.put_full(e.get_fields())
+                elif self._rec_mode not in ("surface", "full"):
                     e.sync()
                 if self.writer is not None and self.writer.error is not None:
                     raise self.writer.error

@@ -84,6 +84,39 @@ def test_plugin_full_field_output_matches_reference_schema(tmp_path):
         assert np.array_equal(r.read(key, frame=9), d[key]), key
 
 
+@pytest.mark.parametrize("every", [1, 3])
+def test_plugin_full_field_ring_and_synchronous_paths_agree(tmp_path, every):
+    """record = "full": frames stream through the recorder ring when they are small (the default for the reference's
+    grid sizes) and are read back synchronously otherwise -- same file either way, and the k = 0 plane of frame t is
+    the reference's surface snapshot of step t + 1."""
+    from phonomena_b200.h5lite import H5Reader
+    d = H.load_golden("crystal_48x32x12")
+    files = []
+    for ring in (True, False):
+        s = make_solver(d, tmp_path, record="full", record_every=every, chunk_steps=7)
+        s.file = str(tmp_path / ("full_%d.h5" % ring))
+        if not ring:
+            s.FULL_RING_MAX_FRAME_BYTES = 0
+        g, m = fake_from_golden(d)
+        s.init(g, m, d["steps"])
+        assert s._full_ring == ring
+        s.run()
+        files.append(s.file)
+    a, b = H5Reader(files[0]), H5Reader(files[1])
+    frames = d["steps"] // every
+    for key in ("ux", "uy", "uz"):
+        assert a.shape(key) == b.shape(key) and a.shape(key)[-1] == frames
+        for t in range(frames):
+            assert np.array_equal(a.read(key, frame=t), b.read(key, frame=t)), (key, t)
+    assert a.attrs["frames_written"] == b.attrs["frames_written"] == frames
+    for n in (int(v) for v in d["snap_steps"]):
+        if n % every == 0:
+            assert np.array_equal(a.read("uz", frame=n // every - 1)[:, :, 0], d["snap_uz_%d" % n]), n
+    if d["steps"] % every == 0:
+        for key in ("ux", "uy", "uz"):
+            assert np.array_equal(a.read(key, frame=frames - 1), d[key]), key
+
+
 def test_plugin_write_mode_off_and_fp32(tmp_path):
     d = H.load_golden("crystal_48x32x12")
     s = make_solver(d, tmp_path, write_mode="off", precision="fp32", arith="fast")
