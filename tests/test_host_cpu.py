@@ -163,3 +163,43 @@ def test_merge_slabs_reassembles_single_gpu_schema(tmp_path):
             assert np.array_equal(r.read(name, frame=t), a[..., t])
     with pytest.raises(ValueError, match="tile"):
         merge_slabs(parts[1:], str(tmp_path / "bad.h5"))
+
+
+def test_h5lite_positional_frames_from_threads(tmp_path):
+    """The plugin's writer path: space preallocated, frames reserved in any order and filled by concurrent
+    positional writes of page-sized pieces; unused preallocated space is dropped at close."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    from phonomena_b200.h5lite import H5Reader, H5Writer
+    rng = np.random.default_rng(3)
+    p = str(tmp_path / "par.h5")
+    shape, frames = (40, 33, 1), 12
+    data = {k: rng.standard_normal(shape + (frames,)) for k in ("ux", "uz")}
+    w = H5Writer(p)
+    w.attrs["dt"] = 0.5
+    w.create_dataset("density", rng.standard_normal((5, 4, 3)))
+    ds = {k: w.create_chunked(k, shape + (frames + 3,)) for k in data}      # three frames never written
+    w.preallocate((frames + 3) * sum(d.frame_bytes + 8 for d in ds.values()) + (1 << 20))
+    w.settle()
+    with ThreadPoolExecutor(4) as pool:
+        jobs = []
+        for t in rng.permutation(frames):
+            for k, d in ds.items():
+                mv = memoryview(np.ascontiguousarray(data[k][..., t]).reshape(-1)).cast("B")
+                pos = w.reserve_frame(d, int(t))
+                for o in range(0, mv.nbytes, 4096):
+                    jobs.append(pool.submit(w.pwrite, mv[o:o + 4096], pos + o))
+        for j in jobs:
+            j.result()
+    with pytest.raises(ValueError):
+        w.reserve_frame(ds["ux"], 0)                    # a frame is written once
+    with pytest.raises(ValueError):
+        w.reserve_frame(ds["ux"], frames + 3)           # outside the dataset
+    w.close()
+    r = H5Reader(p)
+    for k in data:
+        for t in range(frames):
+            assert np.array_equal(r.read(k, frame=t), data[k][..., t]), (k, t)
+    assert r.attrs["dt"] == 0.5 and r.shape("density") == (5, 4, 3)
+    # the file ends where the metadata ends: the preallocated tail is gone
+    assert os.path.getsize(p) < 2 * frames * sum(d.frame_bytes for d in ds.values()) + (1 << 16)
