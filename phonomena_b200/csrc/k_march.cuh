@@ -237,6 +237,7 @@ k_step_march(const __grid_constant__ MarchMaps tm, StepArgs<typename A::T> p, Ma
     constexpr int V = C_::V, SZ = C_::SZ, TZ = C_::TZ, W = C_::W, NT = W * 32;
     constexpr int UCE = C_::UCOMP / SZ, OCE = C_::OCOMP / SZ, XCE = C_::XCOMP / SZ;   // component strides in elements
     static_assert(NST >= C_::NSO, "u_cur ring must be at least as deep as the u_old ring");
+    static_assert((W & (W - 1)) == 0, "the round-robin ring refill takes the warp index modulo a power of two");
     constexpr int ROWE = C_::ROWB / SZ;
     constexpr uint32_t kClsMask = (PHB_DIAG == 2) ? 3u : 255u;   // compute-only timing variant: tiles are never loaded
     using PV = Pack<T, V>;

@@ -540,7 +540,7 @@ struct Engine : IEngine {
         double best_eff = 0;
         // with a halo exchange in flight NCCL CTAs hold a few SMs when the interior launch starts: finer chunks let
         // the block scheduler rebalance instead of ending with a straggler wave (measured: 4 chunks)
-        const int ch_min = (c->nranks > 1 && np >= 64) ? 4 : 1;
+        const int ch_min = (c->nranks > 1 && c->halo != 2 && np >= 64) ? 4 : 1;    // (the fused push has no NCCL kernel beside it)
         for (int ch = ch_min; ch <= 16 && ch * 8 <= np; ++ch) {
             if (ch < 16 && (np + ch - 1) / ch > 256) continue;    // x-spacing table lives in shared memory
             const long long blocks = tiles * ch, waves = (blocks + slots - 1) / slots;
