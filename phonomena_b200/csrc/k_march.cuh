@@ -383,6 +383,7 @@ k_step_march(const __grid_constant__ MarchMaps tm, StepArgs<typename A::T> p, Ma
     int sCi = 0, sNi = 1 % NST;                       // stage indices of plane n and n + 1
     uint32_t phN = 0;                                 // phase parity of full[sNi] for plane n + 1
 
+    bool pushed = false;                              // this thread stored into a neighbour's ghost plane (PUSH)
     constexpr int kUnroll = (RW == 1) ? PHB_UNROLL : PHB_UNROLL_RW2;
 #pragma unroll kUnroll
     for (int it = 0; it + 1 < nplanes; ++it) {
@@ -717,8 +718,8 @@ k_step_march(const __grid_constant__ MarchMaps tm, StepArgs<typename A::T> p, Ma
                             *reinterpret_cast<PV *>(p.push_hi[1] + po) = oy[q];
                             *reinterpret_cast<PV *>(p.push_hi[2] + po) = oz[q];
                         }
-                        __threadfence_system();       // out before the stream-ordered flag write that follows the kernel
                     }
+                    pushed = true;
                 }
             }
         }
@@ -751,6 +752,12 @@ k_step_march(const __grid_constant__ MarchMaps tm, StepArgs<typename A::T> p, Ma
                 t5m[q][e] = t5[q][e]; t6m[q][e] = t6[q][e]; rowc[q][e] = rown[q][e];
             }
         }
+    }
+    // Peer stores are posted writes over NVLink: one system-scope fence per pushing thread at the END of the block
+    // (a fence inside the plane loop stalls the warp for an NVLink round trip per row: 40 us per neighbour and step).
+    // The flag the neighbour waits on is written by k_signal, stream-ordered after this kernel has completed.
+    if constexpr (PUSH) {
+        if (pushed) __threadfence_system();
     }
 }
 

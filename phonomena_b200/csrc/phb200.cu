@@ -525,7 +525,8 @@ struct Engine : IEngine {
         // kernel = auto on a small slab: the x-march is a serial chain per (y, z) tile, and a grid of a few thousand
         // cells has too few tiles to fill the SMs -- one thread per cell is faster there (measured: 32^3 25 vs 33 us per
         // step, equal at 64^3, 2x slower at 96^3; EXACT arithmetic 8x faster on the 31x21x6 default.json grid)
-        if (c->cfg.kernel == PHB_KERNEL_AUTO && (long long)c->cfg.nxl * c->cfg.ny * c->cfg.nz < 200000) return false;
+        // (not for slabs that push their halos from inside the marching kernel)
+        if (c->cfg.kernel == PHB_KERNEL_AUTO && c->halo != 2 && (long long)c->cfg.nxl * c->cfg.ny * c->cfg.nz < 200000) return false;
         return c->maps_ok && march_fits();
     }
     // x-chunks per launch: fill whole waves of (148 SMs x resident blocks) with the (y,z) tiles
