@@ -5,23 +5,29 @@
 //
 //  * The reference stores z fastest, so lanes run along z (V cells per lane, 16-byte
 //    vectors) and the block MARCHES along x, the slowest axis -- the role "z-marching"
-//    plays in the usual 2.5-D blocking.  A block owns a (TY rows x 32*V cells) tile of the
-//    (y, z) plane and a chunk of x-planes; warp r of the block is row j0-1+r, so the first
-//    and last warps are the y-halo rows (they only compute stresses).
+//    plays in the usual 2.5-D blocking.  A block owns an (R rows x 32*V cells) tile of the
+//    (y, z) plane and a chunk of x-planes; the first and last tile rows are the y-halo rows
+//    (stresses only), the TY = R - 2 rows between them produce u_new.
+//  * RW rows per warp (template; production: R = 16, RW = 2 -> 8 warps x 255 registers).  A thread
+//    owns RW x V cells with independent dependency chains; every phase of the plane loop is one
+//    basic block over all rows, so the chains interleave, and the y-exchange, the barrier traffic
+//    and the address arithmetic are paid once per RW rows.  RW = 1 is the 16-warp variant.
 //  * EVERY input arrives by TMA (cp.async.bulk.tensor.4d / .3d -> UTMALDG): per x-plane one stage of
 //    an NST-deep shared ring gets the three u_cur tiles in ONE 4-D transfer (z, y, plane,
 //    component; 16-byte halo vector on each side in z, halo row on each side in y) plus the
 //    1-byte stencil-class tile; the three u_old tiles (no halo, needed only late in the
-//    iteration) use their own 2-deep ring, again one 4-D transfer.  Out-of-range rows / columns /
+//    iteration) use their own ring, again one 4-D transfer.  Out-of-range rows / columns /
 //    planes are zero-filled by the TMA unit, so there is no load-side boundary code and no global
 //    load instruction in the plane loop.  `full[s]` mbarriers signal arrival; `done[s]` (bar_empty,
-//    one arrival per warp) releases a stage.  There is no producer warp: the lane whose arrival
-//    completes `done[s]` finds it complete, claims the next plane with a shared-memory CAS and
-//    issues its TMA loads.  Every issued TMA is waited for by some warp before the block exits.
-//  * There is NO block-wide barrier in the plane loop.  Per plane a row-warp publishes its
-//    T2/T4/T6 (the stresses its y-neighbours need) into a double-buffered exchange tile and
-//    arrives on its two neighbours' `nb[r][parity]` mbarriers; it then waits on its own, once.
-//    The halo rows (first / last warp) compute only what their one neighbour reads.
+//    one arrival per warp) releases a stage.
+//  * Ring refill is round robin: in iteration `it` warp it % W reloads the stage plane it - 1
+//    occupied, between its publish and its neighbour wait (PHB_REFILL == 1).  No producer warp, no
+//    barrier test or counter at the end of a plane, and the extra work never lands on the warp that
+//    is already last.  Every issued TMA is waited for by some warp before the block exits.
+//  * There is NO block-wide barrier in the plane loop.  Per plane a warp publishes T2 of its first
+//    row and T4/T6 of its last row (the stresses its y-neighbour warps need) into a double-buffered
+//    exchange tile and arrives on its two neighbours' `pub[w][parity]` mbarriers; it then waits on
+//    its own, once.  Rows inside a warp exchange through registers.
 //  * Multi-GPU (template PUSH): the first / last owned plane of u_new is also stored into the
 //    neighbours' ghost planes through CUDA-IPC peer pointers (NVLink), see phb200.cu step().
 //  * Per plane a thread keeps in registers, per cell: u(n) (own position), the normal stresses
@@ -31,7 +37,8 @@
 //  * The reference's slice ranges ("never written => 0") are not code here: the per-cell
 //    stencil class (1 byte, fd_common.cuh) selects a 16-entry coefficient row in shared memory
 //    that is already zero wherever a stress or an update does not exist.
-//  * u_new leaves as 16-byte vector stores.
+//  * u_new leaves as 16-byte vector stores; with template ZF the block that owns k = nz-1 then applies
+//    the z = -1 absorbing face to its own results (three scalar re-stores by one lane).
 //
 // Arithmetic goes through the same formula functions as the naive kernel, so in EXACT mode
 // both are bit-identical to the reference.
