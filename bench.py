@@ -233,7 +233,7 @@ def run_b200(args):
     # ---- e2e through the plugin API (reference interface), per rank its slab ------------------
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(case, n, rank, local, K, dtype, arith, dist)
+        e2e = run_e2e(case, n, rank, local, K, dtype, arith, dist, fields=tuple(args.e2e_fields.split(",")))
 
     if rank != 0:
         if dist is not None:
@@ -277,7 +277,7 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
-def run_e2e(case, n, rank, local, K, dtype, arith, dist):
+def run_e2e(case, n, rank, local, K, dtype, arith, dist, fields=("ux", "uy", "uz")):
     """Solver.init + Solver.run through the plugin with host buffers: mesh lines, inclusion list
     and tables go host->device in init(); inside the timed run() every chunk's source samples go
     host->device and every step's surface planes come back through the pinned ring into the HDF5
@@ -289,6 +289,7 @@ def run_e2e(case, n, rank, local, K, dtype, arith, dist):
     s.cfg.update({"precision": {"f64": "fp64", "f32": "fp32"}[dtype], "arith": arith, "device": local, "wave": "sin",
                   "wave_args": {"f": 100}, "write_mode": "thread", "record": "surface", "record_every": 1,
                   "slabs_from_env": n > 1, "chunk_steps": 10,
+                  "record_fields": list(fields),
                   "merge_slabs": False})      # N > 1: one slab file per rank (concatenating them is post-processing)
     # output file: tmpfs when the box has one with room (the run measures the solver and its copies, not the
     # scratch disk of the box), else the temp directory; reported in e2e["file_dir"]
@@ -326,8 +327,9 @@ def run_e2e(case, n, rank, local, K, dtype, arith, dist):
     nx, ny, nz = case.shape
     path = s.file if n == 1 else "%s.rank%d" % (s.file, rank)
     out = {"value": nx * ny * nz * steps / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": 8,
-           "d2h_bytes_per_step": 8 * ((nx - 1) * ny + nx * (ny - 1) + nx * ny), "steps": steps,
-           "what": "Solver.run(): source sample H2D + surface ux,uy,uz planes D2H (pinned ring) -> HDF5 every step"
+           "d2h_bytes_per_step": 8 * sum(v for k, v in (("ux", (nx - 1) * ny), ("uy", nx * (ny - 1)), ("uz", nx * ny)) if k in fields),
+           "steps": steps,
+           "what": "Solver.run(): source sample H2D + surface %s planes D2H (pinned ring) -> HDF5 every step" % ",".join(fields)
                    + ("; one slab file per rank, max over ranks" if n > 1 else ""),
            "file_bytes": os.path.getsize(path), "file_dir": out_dir,
            "writer_finish_ms": 1e3 * s.stats.get("writer_finish_seconds", 0.0),
@@ -367,6 +369,9 @@ def main():
     ap.add_argument("--arith", default="fast", choices=["fast", "exact"])
     ap.add_argument("--kernel", default="auto")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-fields", default="ux,uy,uz",
+                    help="surface components the e2e run records every step (BASELINE config #3 names u_z; default: all three, "
+                         "what the reference's Writer stores)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--extra", action="store_true", help="also time fp32 and fp64-exact on the same grid")
     args = ap.parse_args()

@@ -405,14 +405,15 @@ def merge_slabs(paths, out_path):
     nx = len(np.atleast_1d(rs[0].attrs["x"]))
     if x0 != nx:
         raise ValueError("slab files cover %d of %d planes" % (x0, nx))
-    frames = min(int(r.attrs.get("frames_written", r.shape("uz")[3])) for r in rs)
+    names = [k for k in ("ux", "uy", "uz") if all(k in r.datasets for r in rs)]       # cfg["record_fields"] may drop some
+    frames = min(int(r.attrs.get("frames_written", r.shape(names[0])[3])) for r in rs) if names else 0
     with H5Writer(out_path) as w:
         w.attrs.update(rs[0].attrs)
         w.attrs.update({"x0": 0, "nxl": nx, "frames_written": frames})
         for name in ("density", "elasticity"):
             if all(name in r.datasets for r in rs):
                 w.create_dataset(name, np.concatenate([r.read(name) for r in rs], axis=0))
-        for name in ("ux", "uy", "uz"):
+        for name in names:
             shapes = [r.shape(name) for r in rs]
             full = (sum(sh[0] for sh in shapes),) + tuple(shapes[0][1:3]) + (shapes[0][3],)
             d = w.create_chunked(name, full)

@@ -48,6 +48,7 @@ cfg = {
     "device": 0,                # CUDA device ordinal (one process per GPU; slabs via torchrun, see slab_from_env)
     "record": "surface",        # "surface": uz (and ux, uy) at z-index 0 per step | "full": whole fields | "off"
     "record_every": 1,
+    "record_fields": ["ux", "uy", "uz"],   # which displacement components are recorded (the reference writes all three)
     "chunk_steps": 50,          # steps enqueued per library call (cancel / progress granularity)
     "kernel": "auto",
     "material": "inclusions",   # "inclusions": primary/secondary + inclusion list, filled on the device (what Material.update
@@ -80,7 +81,7 @@ class Writer:
     PARALLEL_MIN_BYTES = 1 << 19
     PREALLOCATE_MAX_BYTES = 2 << 30
 
-    def __init__(self, path, engine, meta, frames, mode, record_every, ring=True):
+    def __init__(self, path, engine, meta, frames, mode, record_every, ring=True, fields=("ux", "uy", "uz")):
         self.path, self.e, self.mode, self.frames = path, engine, mode, frames
         self.ring = ring or mode == "surface"      # frames arrive through the device / pinned ring (else: put_full)
         self.h5 = H5Writer(path)
@@ -93,11 +94,9 @@ class Writer:
         ny, nz = engine.ny, engine.nz
         zext = 1 if mode == "surface" else None
         # x extents are the planes this context owns (the whole grid, or one slab: attrs x0 / nxl)
-        self.ds = {
-            "ux": self.h5.create_chunked("ux", (engine.planes(0), ny, zext or nz, frames)),
-            "uy": self.h5.create_chunked("uy", (engine.planes(1), ny - 1, zext or nz, frames)),
-            "uz": self.h5.create_chunked("uz", (engine.planes(2), ny, zext or (nz - 1), frames)),
-        }
+        shapes = {"ux": (engine.planes(0), ny, zext or nz, frames), "uy": (engine.planes(1), ny - 1, zext or nz, frames),
+                  "uz": (engine.planes(2), ny, zext or (nz - 1), frames)}
+        self.ds = {k: self.h5.create_chunked(k, shapes[k]) for k in ("ux", "uy", "uz") if k in fields}
         # The static datasets (density alone is Nx*Ny*Nz doubles) are pushed out now, in init(), like the reference's
         # Writer.init (base_solver.py:105-133): otherwise the kernel's dirty-page writeback of them throttles the
         # frame appends of the stepping loop.
@@ -159,7 +158,8 @@ class Writer:
     # full mode: called synchronously by the run loop
     def put_full(self, fields):
         for name, a in zip(("ux", "uy", "uz"), fields):
-            self.h5.write_frame(self.ds[name], self.written, a)
+            if name in self.ds:
+                self.h5.write_frame(self.ds[name], self.written, a)
         self.written += 1
 
     def finish(self, timeout=300.0):
@@ -228,15 +228,19 @@ class Solver:
         rec_mode = c["record"] if c.get("write_mode", "off") != "off" else "off"
         x0, nxl, rank, nranks = slab_from_env(x.size) if c.get("slabs_from_env") else (0, x.size, 0, 1)
         rec_mask, ring_slots = 0, 32
+        fields = tuple(k for k in ("ux", "uy", "uz") if k in c.get("record_fields", ("ux", "uy", "uz")))
+        if rec_mode != "off" and not fields:
+            raise ValueError("record_fields selects none of ux, uy, uz")
+        fmask = sum(b for k, b in (("ux", _lib.REC_UX), ("uy", _lib.REC_UY), ("uz", _lib.REC_UZ)) if k in fields)
         if rec_mode == "surface":
-            rec_mask = _lib.REC_UX | _lib.REC_UY | _lib.REC_UZ
+            rec_mask = fmask
         elif rec_mode == "full":
             # whole arrays every recorded step (the reference's Writer, base_solver.py:97-100,135-160): when a frame is
             # small enough they go through the same device ring -> pinned ring -> writer thread as the surface planes,
             # so the stepping loop never waits for a read-back; big grids keep the synchronous get_fields path
-            fbytes = 8 * nxl * y.size * z.size * 3
+            fbytes = 8 * nxl * y.size * z.size * len(fields)
             if fbytes <= self.FULL_RING_MAX_FRAME_BYTES:
-                rec_mask = _lib.REC_UX | _lib.REC_UY | _lib.REC_UZ | _lib.REC_FULL
+                rec_mask = fmask | _lib.REC_FULL
                 ring_slots = int(max(4, min(32, (256 << 20) // max(1, fbytes))))
         self._full_ring = bool(rec_mask & _lib.REC_FULL)
         e = _lib.Engine(x.size, y.size, z.size, dt, d2=dt ** 2,
@@ -291,7 +295,7 @@ class Solver:
             if rec_mode == "full" and P.size <= 1 << 22:      # the reference's `elasticity` is 288 B/cell
                 meta["elasticity"] = np.array(C_out, np.float64) if dense else np.where((ids == 1)[..., None, None], sec["c"], prim["c"])
             path = self.file if nranks == 1 else "%s.rank%d" % (self.file, rank)      # one file per slab
-            self.writer = Writer(path, e, meta, frames, rec_mode, int(c["record_every"]), ring=self._full_ring)
+            self.writer = Writer(path, e, meta, frames, rec_mode, int(c["record_every"]), ring=self._full_ring, fields=fields)
             self.writer.start()
         self._rec_mode = rec_mode
 

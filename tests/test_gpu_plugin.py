@@ -213,3 +213,25 @@ def test_plugin_material_arrays_errors(tmp_path):
     g, m = _arrays_material(d, C, P)
     with pytest.raises(Exception, match="distinct materials"):
         s.init(g, m, 2)
+
+
+def test_plugin_record_fields_subset(tmp_path):
+    """cfg["record_fields"]: only the selected components are recorded (BASELINE config #3 records surface u_z)."""
+    from phonomena_b200.h5lite import H5Reader
+    d = H.load_golden("default_json_1000")
+    for mode in ("surface", "full"):
+        s = make_solver(d, tmp_path, record=mode, record_fields=["uz"], record_every=100)
+        s.file = str(tmp_path / ("uz_%s.h5" % mode))
+        g, m = fake_from_golden(d)
+        s.init(g, m, d["steps"])
+        s.run()
+        r = H5Reader(s.file)
+        assert "uz" in r.datasets and "ux" not in r.datasets and "uy" not in r.datasets
+        assert r.shape("uz")[-1] == d["steps"] // 100
+        last = r.read("uz", frame=d["steps"] // 100 - 1)
+        assert np.array_equal(last[:, :, 0], d["uz"][:, :, 0])
+        if mode == "full":
+            assert np.array_equal(last, d["uz"])
+    with pytest.raises(ValueError):
+        s = make_solver(d, tmp_path, record_fields=[])
+        s.init(*fake_from_golden(d), 10)
