@@ -15,7 +15,8 @@ One JSON line on rank 0:
              fields resident in HBM
   e2e        the same metric through the plugin API (Solver.init + Solver.run, reference interface),
              wall clock of run(): per step the source sample goes host->device and the recorded
-             surface planes (ux, uy, uz at z-index 0) come device->pinned host->HDF5 file
+             surface plane (uz at z-index 0, BASELINE config #3; --e2e-fields ux,uy,uz for all three)
+             comes device->pinned host->HDF5 file
   roofline   dominant kernel (k_step_march): algorithmic bytes (73 B/cell fp64: 9 field words + 1
              class byte) / measured kernel time, against MEASURED_PEAKS.json hbm_gbs
   cpu_baseline  the NumPy oracle (restatement of the reference's NumPy solver) on a bounded sample
@@ -369,9 +370,9 @@ def main():
     ap.add_argument("--arith", default="fast", choices=["fast", "exact"])
     ap.add_argument("--kernel", default="auto")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-fields", default="ux,uy,uz",
-                    help="surface components the e2e run records every step (BASELINE config #3 names u_z; default: all three, "
-                         "what the reference's Writer stores)")
+    ap.add_argument("--e2e-fields", default="uz",
+                    help="surface components the e2e run records every step: BASELINE config #3 is 'surface u_z HDF5 recording' "
+                         "(default); ux,uy,uz = everything the reference's Writer stores at the surface")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--extra", action="store_true", help="also time fp32 and fp64-exact on the same grid")
     args = ap.parse_args()
