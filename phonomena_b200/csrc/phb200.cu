@@ -514,8 +514,8 @@ struct Engine : IEngine {
     // lane: nz a multiple of the vector width, and not in the first lane of a tile (V = 2 reads the lane before)
     bool zface_fused() const {
         const int V = VecOf<T>::V, nz = c->cfg.nz;
-        // measured at 512^3: fp32 gains 4 % (the separate strided face kernel costs 48 us per step), fp64 loses as much in
-        // the stencil kernel itself as the face kernel costs -> default on for fp32 only (PHB_ZFUSE=0/1 overrides)
+        // measured at 512^3: fp32 gains 4 % (the separate strided face kernel costs 48 us per step), fp64 loses about as much
+        // in the stencil kernel itself as the face kernel costs -> default on for fp32 only (PHB_ZFUSE=0/1 overrides)
         const bool want = c->zfuse < 0 ? (sizeof(T) == 4) : (c->zfuse != 0);
         if (!want || comp() || c->mRW != 2 || nz < 2 * V || nz % V != 0) return false;
         return ((nz - 1) % (32 * V)) / V >= 1;
