@@ -203,3 +203,61 @@ def test_h5lite_positional_frames_from_threads(tmp_path):
     assert r.attrs["dt"] == 0.5 and r.shape("density") == (5, 4, 3)
     # the file ends where the metadata ends: the preallocated tail is gone
     assert os.path.getsize(p) < 2 * frames * sum(d.frame_bytes for d in ds.values()) + (1 << 16)
+
+
+class _FakeRingEngine:
+    """Stands in for _lib.Engine on the CPU: hands the plugin's Writer a scripted sequence of recorder frames
+    (the real one returns views into the pinned ring; record_next / record_release keep the same contract)."""
+
+    def __init__(self, nx, ny, nz, frames, fields, full, rng):
+        self.nx, self.ny, self.nz, self.x0, self.nxl = nx, ny, nz, 0, nx
+        shp = {"ux": (nx - 1, ny), "uy": (nx, ny - 1), "uz": (nx, ny)}
+        zext = {"ux": nz, "uy": nz, "uz": nz - 1}
+        self.data = [{k: rng.standard_normal(shp[k] + ((zext[k],) if full else ())) for k in fields} for _ in range(frames)]
+        self.next, self.held, self.released = 0, False, 0
+
+    def planes(self, comp):
+        return self.nx - 1 if comp == 0 else self.nx
+
+    def record_next(self, timeout_ms=0):
+        assert not self.held, "record_next called again before record_release"
+        if self.next >= len(self.data):
+            return None
+        self.held = True
+        self.next += 1
+        return self.next - 1, self.data[self.next - 1]
+
+    def record_release(self):
+        assert self.held
+        self.held = False
+        self.released += 1
+
+
+@pytest.mark.parametrize("full,fields,parallel", [(False, ("ux", "uy", "uz"), True), (False, ("uz",), False),
+                                                   (True, ("ux", "uy", "uz"), True), (True, ("uy", "uz"), False)])
+def test_plugin_writer_thread_on_scripted_frames(tmp_path, full, fields, parallel):
+    """The plugin's Writer (ring consumer thread, preallocation, piecewise parallel positional writes above
+    PARALLEL_MIN_BYTES, one write below it, record_fields subsets) against a scripted frame source: the file holds
+    every frame in order, with the reference's dataset shapes (z extent 1 in surface mode)."""
+    from phonomena_b200.h5lite import H5Reader
+    from phonomena_b200.solver_b200 import Writer
+    rng = np.random.default_rng(11)
+    nx, ny, nz, frames = 9, 8, 5, 7
+    eng = _FakeRingEngine(nx, ny, nz, frames, fields, full, rng)
+    meta = {"attrs": {"dt": 0.25, "x": np.arange(nx, dtype=float)}, "density": rng.standard_normal((nx, ny, nz)), "elasticity": None}
+    w = Writer(str(tmp_path / "w.h5"), eng, meta, frames, "full" if full else "surface", 1, ring=True, fields=fields)
+    if parallel:
+        w.PARALLEL_MIN_BYTES = 64          # force the multi-piece path on these tiny frames
+    w.start()
+    w.finish()
+    assert w.error is None and w.written == frames and eng.released == frames
+    r = H5Reader(w.path)
+    assert sorted(k for k in r.datasets if k.startswith("u")) == sorted(fields)
+    assert r.attrs["frames_written"] == frames and r.attrs["record"] == ("full" if full else "surface")
+    for k in fields:
+        exp_shape = eng.data[0][k].shape + (() if full else (1,)) + (frames,)
+        assert r.shape(k) == exp_shape, (k, r.shape(k), exp_shape)
+        for t in range(frames):
+            got = r.read(k, frame=t)
+            assert np.array_equal(got if full else got[..., 0], eng.data[t][k]), (k, t)
+    assert np.array_equal(r.read("density"), meta["density"])
