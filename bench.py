@@ -134,6 +134,12 @@ def cpu_sample_c(steps, warmup, n=256):
             "sample": "%d^3 block of the same crystal, %d steps, C + OpenMP (gcc -O2 -ffp-contract=off), float64" % (n, steps)}
 
 
+def workload_name(n):
+    """The workload both arms report (the reference arm times a bounded sample of it)."""
+    return ("phononic crystal %dx%dx%d (Au cylinders pitch 32 r 8 in GaAs; BASELINE config #%s), x-slabs of %d planes/GPU, "
+            "Mur ABC + free surface + left-wall sin source f=100, courant 0.1" % (NX_PER_GPU * n, NY, NZ, "3" if n == 1 else "5", NX_PER_GPU))
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path = NumPy slicing
     arithmetic, timed through the oracle port (the reference is pure Python and does not travel to
@@ -143,19 +149,19 @@ def run_reference(args):
     if rank != 0:
         return
     threads = max(1, min(6, len(os.sched_getaffinity(0))))
-    steps, warmup = max(1, min(args.steps, 10)), max(1, min(args.warmup, 2))
+    steps, warmup = max(1, min(args.steps, 200)), max(1, min(args.warmup, 10))    # ~0.12 s per 128^3 step: K = 50 is 6 s
     v, sample = cpu_sample(threads, steps, warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
         "ms_per_step": 128 ** 3 / v / 1e6, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "phononic crystal (Au cylinders pitch 32 r 8 in GaAs), bounded sample: " + sample},
+        "config": {"workload": workload_name(max(1, args.gpus)), "sample": sample},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "host": {"cpu_count": os.cpu_count(), "affinity": len(os.sched_getaffinity(0)), "numpy": np.__version__},
     }
     try:
-        line["extra"] = {"c_openmp_port": cpu_sample_c(steps, 1)}
+        line["extra"] = {"c_openmp_port": cpu_sample_c(min(steps, 10), 1)}
     except Exception as exc:      # context only
         line["extra"] = {"c_openmp_port": {"error": str(exc)[:200]}}
     print(json.dumps(line), flush=True)
@@ -254,8 +260,7 @@ def run_b200(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n, "steps": K, "warmup": W, "ms_per_step": ms / K,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
-        "config": {"workload": "phononic crystal %dx%dx%d (Au cylinders pitch 32 r 8 in GaAs; BASELINE config #%s), x-slabs of %d planes/GPU, "
-                               "Mur ABC + free surface + left-wall sin source f=100, courant 0.1" % (nx, NY, NZ, "3" if n == 1 else "5", NX_PER_GPU),
+        "config": {"workload": workload_name(n),
                    "arith": arith, "material": "indexed (1-byte stencil class)", "kernel": info["kernel"],
                    "l2": "inputs (%.1f GB/GPU) far exceed the 126 MB L2; no explicit flush" % (info["device_bytes"] / 1e9),
                    "halo": {"none": "none", "nccl": "NCCL send/recv of 3 planes per direction per step, overlapped with the interior update",
