@@ -173,6 +173,35 @@ int phb_p2p_import(phb_ctx *ctx, int32_t rank, int32_t nranks, const char *left,
 int phb_record_next(phb_ctx *ctx, const double **frame, int64_t *tt, int32_t timeout_ms);
 int phb_record_release(phb_ctx *ctx);
 int phb_record_frame_doubles(phb_ctx *ctx, int64_t *n);
+/* Both sides of the ring are bounded, like the reference's writer queue (queue.get(timeout=120) and
+ * join(300), base_solver.py:89-92,148,274): phb_run waits at most `timeout_ms` (default 120 000, or
+ * $PHB_REC_TIMEOUT_MS) for a free slot and then fails; a consumer that cannot go on (e.g. ENOSPC) calls
+ * phb_record_abort, which makes the waiting / next phb_run fail with that message instead of hanging.
+ * Neither call takes the context lock: they are meant to be called while phb_run is blocked. */
+int phb_record_abort(phb_ctx *ctx, const char *why);
+int phb_record_timeout(phb_ctx *ctx, int32_t timeout_ms);
+
+/* replaces: BaseSolver.cancel (base_solver.py:246-248,282-284: a threading.Event polled once per step).
+ * Callable from any thread while phb_run is executing: phb_run returns 3 ("cancelled") after the step in
+ * flight -- also when it is waiting for a free recorder slot.  Does not take the context lock. */
+int phb_cancel(phb_ctx *ctx);
+
+/* replaces: Writer.run (base_solver.py:135-160), the consumer thread / process that stores one time slab
+ * per queue item.  `nthreads` native threads drain the pinned ring: frame f (the f-th recorded frame) has
+ * its component c written with pwrite(fd, ...) from the pinned slot to file offset base[c] + f * stride
+ * (bytes[c] bytes; components in the ring's order ux, uy, uz as selected by record_mask) -- the chunk
+ * addresses the host-side HDF5 writer reserved before the run.  `fd` stays owned by the caller and must
+ * stay open until phb_writer_finish has returned.  A write error aborts the recording (phb_run then fails
+ * with the errno text).  phb_writer_finish: no further frame will be produced; drain, join (at most
+ * timeout_ms; 0 = 300 s), report the number of frames written and the seconds the threads spent waiting
+ * for frames / writing them.  phb_destroy joins a writer that is still running. */
+int phb_writer_start(phb_ctx *ctx, int32_t fd, int32_t ncomp, const int64_t *base, const int64_t *bytes,
+                     int64_t stride, int64_t frames, int32_t nthreads);
+int phb_writer_finish(phb_ctx *ctx, int32_t timeout_ms, int64_t *written, double *wait_s, double *write_s);
+/* host-only exercise of the ring + writer threads (CPU tests; makes no CUDA call): a producer thread
+ * pushes `frames` synthetic frames (element q of frame f = f * 1e6 + q) through a `slots`-deep ring. */
+int phb_writer_selftest(int32_t fd, int32_t ncomp, const int64_t *base, const int64_t *bytes, int64_t stride,
+                        int64_t frames, int32_t slots, int32_t nthreads, int32_t timeout_ms, int64_t *written);
 
 /* line probes and on-device spectra.
  * replaces: simulation/analysis.py:59-66 -- the reference re-reads the (x, t) matrix

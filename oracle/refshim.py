@@ -1,9 +1,10 @@
 """Import the UNMODIFIED reference solver in the build container -- TEST INFRASTRUCTURE ONLY.
 
-``/root/reference`` exists only in the build container, never on the GPU box, so
-this module is used by ``oracle/gen_golden.py`` (fixture generation) and by the
-CPU-only tests that are skipped when the reference is absent.  Nothing in the
-product imports it.
+``/root/reference`` exists only in the build container; ``make -C oracle ref`` stages an
+unmodified copy of the solver package in the git-ignored ``oracle/_ref/``, which travels to the GPU
+box.  This module is used by ``oracle/gen_golden.py`` (fixture generation), by ``oracle/ref_bench.py``
+(the timed CPU baseline of ``bench.py --impl reference``) and by the tests marked ``ref`` (skipped when
+neither copy is present).  Nothing in the product imports it.
 
 Three shims, no edits to the reference:
   1. stub ``PyQt5.QtCore`` (``gui/worker.py`` only needs QObject/QRunnable/pyqtSignal/pyqtSlot)
@@ -17,7 +18,17 @@ import types
 
 import numpy as np
 
-REF_ROOT = os.environ.get("PHONOMENA_REF", "/root/reference")
+def _find_root():
+    """$PHONOMENA_REF, the read-only checkout of the build container, or the copy `make -C oracle ref` staged in
+    the git-ignored oracle/_ref/ (which travels to the GPU box)."""
+    cands = [os.environ.get("PHONOMENA_REF"), "/root/reference", os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")]
+    for c in cands:
+        if c and os.path.isdir(os.path.join(c, "phonomena", "simulation")):
+            return c
+    return cands[1]
+
+
+REF_ROOT = _find_root()
 
 
 def available():

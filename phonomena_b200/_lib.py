@@ -27,12 +27,17 @@ SYMBOLS = (
     "phb_get_material_ids", "phb_set_abc", "phb_set_source_table", "phb_set_fields", "phb_get_fields",
     "phb_get_stress", "phb_run", "phb_sync", "phb_run_timed", "phb_steps_done", "phb_launch_count",
     "phb_info", "phb_profile", "phb_comm_unique_id", "phb_comm_init", "phb_p2p_export", "phb_p2p_import", "phb_record_next", "phb_record_release",
-    "phb_record_frame_doubles", "phb_probe_add", "phb_probe_shape", "phb_probe_read", "phb_probe_dft_t", "phb_probe_dft_xt",
+    "phb_record_frame_doubles", "phb_record_abort", "phb_record_timeout", "phb_cancel", "phb_writer_start", "phb_writer_finish",
+    "phb_writer_selftest", "phb_probe_add", "phb_probe_shape", "phb_probe_read", "phb_probe_dft_t", "phb_probe_dft_xt",
 )
 
 
 class PhbError(RuntimeError):
     pass
+
+
+class PhbCancelled(PhbError):
+    """phb_run returned because phb_cancel was called (not an error for the plugin's run loop)."""
 
 
 class Cfg(C.Structure):
@@ -91,6 +96,13 @@ def load_library(path=None):
     lib.phb_record_next.argtypes = [vp, C.POINTER(dp), C.POINTER(C.c_int64), C.c_int32]
     lib.phb_record_release.argtypes = [vp]
     lib.phb_record_frame_doubles.argtypes = [vp, C.POINTER(C.c_int64)]
+    i64p = C.POINTER(C.c_int64)
+    lib.phb_record_abort.argtypes = [vp, C.c_char_p]
+    lib.phb_record_timeout.argtypes = [vp, C.c_int32]
+    lib.phb_cancel.argtypes = [vp]
+    lib.phb_writer_start.argtypes = [vp, C.c_int32, C.c_int32, i64p, i64p, C.c_int64, C.c_int64, C.c_int32]
+    lib.phb_writer_finish.argtypes = [vp, C.c_int32, i64p, dp, dp]
+    lib.phb_writer_selftest.argtypes = [C.c_int32, C.c_int32, i64p, i64p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, i64p]
     lib.phb_probe_add.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.POINTER(C.c_int32)]
     lib.phb_probe_shape.argtypes = [vp, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     lib.phb_probe_read.argtypes = [vp, C.c_int32, dp]
@@ -126,6 +138,19 @@ def device_count():
     n = C.c_int(0)
     lib.phb_device_count(C.byref(n))
     return n.value
+
+
+def writer_selftest(fd, base, nbytes, stride, frames, slots=4, nthreads=2, timeout_ms=2000):
+    """Host-only run of the recorder ring + native writer threads (no CUDA call); returns frames written."""
+    lib = load_library()
+    n = len(base)
+    b = (C.c_int64 * n)(*[int(v) for v in base])
+    nb = (C.c_int64 * n)(*[int(v) for v in nbytes])
+    w = C.c_int64(0)
+    rc = lib.phb_writer_selftest(int(fd), n, b, nb, int(stride), int(frames), int(slots), int(nthreads), int(timeout_ms), C.byref(w))
+    if rc != 0:
+        raise PhbError("%s (after %d frames)" % (lib.phb_last_error().decode("utf-8", "replace"), w.value))
+    return w.value
 
 
 def comm_unique_id():
@@ -261,7 +286,15 @@ class Engine:
 
     # -- stepping -----------------------------------------------------------------------
     def run(self, nsteps):
-        _chk(self.lib, self.lib.phb_run(self._ctx, int(nsteps)))
+        rc = self.lib.phb_run(self._ctx, int(nsteps))
+        if rc == 3:
+            raise PhbCancelled("cancelled")
+        _chk(self.lib, rc)
+
+    def cancel(self):
+        """Make the phb_run in progress (on another thread) return after the current step."""
+        if self._ctx:
+            self.lib.phb_cancel(self._ctx)
 
     def sync(self):
         _chk(self.lib, self.lib.phb_sync(self._ctx))
@@ -319,12 +352,19 @@ class Engine:
         if nranks == 1:
             return "none"
         if mode == "p2p":
-            ok = 1
+            # every rank runs the same two collectives whatever fails locally (a rank that skipped one would pair
+            # its next all-gather with the others' previous one)
             try:
-                exports = allgather(self.p2p_export())
-                self.p2p_import(rank, nranks, exports)
+                mine = self.p2p_export()
             except PhbError:
-                ok = 0
+                mine = None
+            exports = allgather(mine)
+            ok = int(all(x is not None for x in exports))
+            if ok:
+                try:
+                    self.p2p_import(rank, nranks, exports)
+                except PhbError:
+                    ok = 0
             if all(allgather(ok)):
                 return "p2p"
         self.comm_init(broadcast(comm_unique_id() if rank == 0 else None), rank, nranks)
@@ -367,6 +407,29 @@ class Engine:
 
     def record_release(self):
         _chk(self.lib, self.lib.phb_record_release(self._ctx))
+
+    def record_abort(self, why="aborted by the consumer"):
+        if self._ctx:
+            self.lib.phb_record_abort(self._ctx, str(why).encode("utf-8", "replace")[:500])
+
+    def record_timeout(self, timeout_ms):
+        _chk(self.lib, self.lib.phb_record_timeout(self._ctx, int(timeout_ms)))
+
+    def writer_start(self, fd, base, nbytes, stride, frames, nthreads=4):
+        """Native writer threads: component c of recorded frame f goes to file offset base[c] + f * stride."""
+        n = len(base)
+        b = (C.c_int64 * n)(*[int(v) for v in base])
+        nb = (C.c_int64 * n)(*[int(v) for v in nbytes])
+        _chk(self.lib, self.lib.phb_writer_start(self._ctx, int(fd), n, b, nb, int(stride), int(frames), int(nthreads)))
+
+    def writer_finish(self, timeout_ms=300000):
+        """Drain + join; returns (frames written, seconds waiting for frames, seconds writing).  Raises on a
+        write error or timeout; the counters are also left in self.writer_stats."""
+        n, wa, wr = C.c_int64(0), C.c_double(0), C.c_double(0)
+        rc = self.lib.phb_writer_finish(self._ctx, int(timeout_ms), C.byref(n), C.byref(wa), C.byref(wr))
+        self.writer_stats = (n.value, wa.value, wr.value)
+        _chk(self.lib, rc)
+        return self.writer_stats
 
     # ---- line probes and on-device spectra (include/phb200.h "line probes") ----
     def probe_add(self, comp, j, k, capacity):

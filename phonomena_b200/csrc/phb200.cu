@@ -27,6 +27,7 @@
 #include "k_march.cuh"
 #include "k_probe.cuh"
 #include "k_naive.cuh"
+#include "rec_ring.h"
 
 using namespace phb;
 
@@ -157,17 +158,15 @@ struct phb_ctx {
     int peer_nxl[2] = {0, 0};
     int *flags = nullptr;        // [0] written by the left neighbour, [1] by the right one: last step pushed
     int *peer_flags[2] = {};     // the neighbours' flag arrays, mapped
-    // recorder
-    double *ring = nullptr;    // pinned host, mapped
+    // recorder: pinned host ring (rec_ring.h) filled through a device staging ring; drained by the native writer
+    // threads (phb_writer_start) or by the caller (phb_record_next / phb_record_release)
+    RecRing rec;
+    NativeWriter wr;
     double *ring_dev = nullptr;   // device staging ring (same slots): the gather kernel runs at HBM speed,
                                   // the D2H copy to the pinned ring runs on its own stream behind it
     cudaStream_t rst = nullptr;
     std::vector<cudaEvent_t> stage_ev;
-    long long frame_doubles = 0;
-    int slots = 0;
-    std::vector<cudaEvent_t> slot_ev;
-    std::vector<long long> slot_tt;
-    std::atomic<long long> produced{0}, consumed{0}, released{0};
+    std::atomic<int> cancel{0};   // phb_cancel: the running / next phb_run returns after the current step
     // marching kernel: TMA descriptors per [buffer][component], tile plan
     MarchMaps mm[3];           // indexed by the buffer that holds u_cur
     bool maps_ok = false;
@@ -754,11 +753,17 @@ struct Engine : IEngine {
 // recorder
 // ------------------------------------------------------------------------------------------
 static int record_frame(phb_ctx *c) {
-    // flow control: wait for a free slot
-    while (c->produced.load() - c->released.load() >= c->slots) std::this_thread::sleep_for(std::chrono::microseconds(50));
-    const long long f = c->produced.load();
-    const int s = (int)(f % c->slots);
-    double *slot = c->ring_dev + (long long)s * c->frame_doubles;
+    // flow control: wait for a free slot -- bounded, and the consumer (or phb_cancel) can break it: the reference
+    // bounds both sides of its writer queue the same way (base_solver.py:89-92,148,274)
+    switch (c->rec.wait_free(&c->cancel)) {
+        case 0: break;
+        case 1: return fail("recording aborted: %s", c->rec.why().c_str());
+        case 3: return 0;      // cancelled: run_locked reports it
+        default: return fail("recorder ring full for %d ms: the frame consumer has stalled (phb_record_timeout)", c->rec.timeout_ms.load());
+    }
+    const long long f = c->rec.produced.load();
+    const int s = (int)(f % c->rec.slots);
+    double *slot = c->ring_dev + (long long)s * c->rec.frame_doubles;
     const int npx = std::max(0, std::min(c->cfg.x0 + c->cfg.nxl, c->cfg.nx - 1) - c->cfg.x0), npyz = c->cfg.nxl;
     if (c->cfg.record_mask & PHB_REC_FULL) {
         // whole arrays in the reference's shapes, one coalesced gather per component (the kernel get_fields uses)
@@ -792,11 +797,11 @@ static int record_frame(phb_ctx *c) {
     CU(cudaGetLastError());
     CU(cudaEventRecord(c->stage_ev[s], c->st));
     CU(cudaStreamWaitEvent(c->rst, c->stage_ev[s], 0));
-    CU(cudaMemcpyAsync(c->ring + (long long)s * c->frame_doubles, slot, (size_t)c->frame_doubles * sizeof(double),
+    CU(cudaMemcpyAsync(c->rec.host + (long long)s * c->rec.frame_doubles, slot, (size_t)c->rec.frame_doubles * sizeof(double),
                        cudaMemcpyDeviceToHost, c->rst));
-    CU(cudaEventRecord(c->slot_ev[s], c->rst));
-    c->slot_tt[s] = c->tt - 1;
-    c->produced.fetch_add(1);
+    CU(cudaEventRecord(c->rec.slot_ev[s], c->rst));
+    c->rec.slot_tt[s] = c->tt - 1;
+    c->rec.produced.fetch_add(1);
     return 0;
 }
 
@@ -935,17 +940,20 @@ int phb_create(const phb_cfg *cfg, phb_ctx **out) {
         if (cfg->record_mask & PHB_REC_UY) fd += (long long)cfg->nxl * (cfg->ny - 1) * (full ? cfg->nz : 1);
         if (cfg->record_mask & PHB_REC_UZ) fd += (long long)cfg->nxl * cfg->ny * (full ? cfg->nz - 1 : 1);
         if (fd <= 0) return cleanup(fail("record_mask %d selects no component", cfg->record_mask));
-        c->frame_doubles = fd;
-        c->slots = cfg->ring_slots > 0 ? cfg->ring_slots : 16;
-        if (cudaHostAlloc((void **)&c->ring, (size_t)c->slots * fd * sizeof(double), cudaHostAllocDefault) != cudaSuccess)
-            return cleanup(fail("cudaHostAlloc of the %d-slot recorder ring failed", c->slots));
-        if (dmalloc(c, (void **)&c->ring_dev, (size_t)c->slots * fd * sizeof(double), false)) return cleanup(1);
+        c->rec.frame_doubles = fd;
+        c->rec.slots = cfg->ring_slots > 0 ? cfg->ring_slots : 16;
+        c->rec.device = c->device;
+        if (const char *e = getenv("PHB_REC_TIMEOUT_MS")) c->rec.timeout_ms.store(atoi(e));
+        if (cudaHostAlloc((void **)&c->rec.host, (size_t)c->rec.slots * fd * sizeof(double), cudaHostAllocDefault) != cudaSuccess)
+            return cleanup(fail("cudaHostAlloc of the %d-slot recorder ring failed", c->rec.slots));
+        if (dmalloc(c, (void **)&c->ring_dev, (size_t)c->rec.slots * fd * sizeof(double), false)) return cleanup(1);
         if (cudaStreamCreateWithFlags(&c->rst, cudaStreamNonBlocking) != cudaSuccess) return cleanup(fail("stream create failed"));
-        c->slot_ev.resize(c->slots);
-        c->stage_ev.resize(c->slots);
+        c->rec.slot_ev.resize(c->rec.slots);
+        c->stage_ev.resize(c->rec.slots);
         for (auto &ev : c->stage_ev) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
-        c->slot_tt.assign(c->slots, -1);
-        for (auto &ev : c->slot_ev) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+        c->rec.slot_tt.assign(c->rec.slots, -1);
+        c->rec.slot_done.assign(c->rec.slots, 0);
+        for (auto &ev : c->rec.slot_ev) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     }
     if (cudaStreamSynchronize(c->st) != cudaSuccess) return cleanup(fail("device init failed: %s", cudaGetErrorString(cudaGetLastError())));
     *out = c;
@@ -954,6 +962,10 @@ int phb_create(const phb_cfg *cfg, phb_ctx **out) {
 
 int phb_destroy(phb_ctx *c) {
     if (!c) return 0;
+    // writer threads read the pinned ring: stop and join them before anything is freed (a context destroyed with a
+    // live consumer was a use-after-free); a caller blocked in phb_record_next sees the abort and returns
+    c->rec.abort("context destroyed");
+    c->wr.finish(2000);
     cudaSetDevice(c->device);
     if (c->st) cudaStreamSynchronize(c->st);
     if (c->cst) cudaStreamSynchronize(c->cst);
@@ -969,8 +981,8 @@ int phb_destroy(phb_ctx *c) {
     graph_invalidate(c);
     if (c->w) cudaFree(c->w);
     cudaFree(c->src_idx);
-    if (c->ring) cudaFreeHost(c->ring);
-    for (auto &ev : c->slot_ev) cudaEventDestroy(ev);
+    if (c->rec.host) cudaFreeHost(c->rec.host);
+    for (auto &ev : c->rec.slot_ev) cudaEventDestroy(ev);
     for (auto &ev : c->stage_ev) cudaEventDestroy(ev);
     if (c->rst) { cudaStreamSynchronize(c->rst); cudaStreamDestroy(c->rst); }
     cudaFree(c->ring_dev);
@@ -1198,7 +1210,13 @@ static int run_locked(phb_ctx *c, int64_t nsteps) {
     if (!c->code) return fail("material not set (table + ids)");
     if (!c->have_abc) return fail("phb_set_abc not called");
     if (c->nranks > 1 && !c->comm && c->halo != 2) return fail("slab context without halo exchange: call phb_comm_init or phb_p2p_import");
+    if (c->cfg.record_mask && c->rec.aborted.load()) return fail("recording aborted: %s", c->rec.why().c_str());
     for (int64_t s = 0; s < nsteps; ++s) {
+        if (c->cancel.load()) {        // phb_cancel from another thread (BaseSolver.cancel, base_solver.py:246-248,282-284)
+            c->cancel.store(0);
+            g_err = "cancelled";
+            return 3;
+        }
         OK(c->eng->step());
         if ((c->tt % c->cfg.record_every) == 0) {
             if (c->cfg.record_mask) OK(record_frame(c));
@@ -1345,14 +1363,17 @@ int phb_p2p_import(phb_ctx *c, int32_t rank, int32_t nranks, const char *left, i
 
 int phb_record_frame_doubles(phb_ctx *c, int64_t *n) {
     if (!c) return fail("null context");
-    *n = c->frame_doubles;
+    *n = c->rec.frame_doubles;
     return 0;
 }
 int phb_record_next(phb_ctx *c, const double **frame, int64_t *tt, int32_t timeout_ms) {
-    if (!c || !c->ring) return fail("recording not enabled");
-    if (c->consumed.load() != c->released.load()) return fail("previous frame not released");
+    if (!c || !c->rec.host) return fail("recording not enabled");
+    if (c->wr.started) return fail("the native writer is draining the ring (phb_writer_start)");
+    RecRing &r = c->rec;
+    if (r.consumed.load() != r.released.load()) return fail("previous frame not released");
     auto t0 = std::chrono::steady_clock::now();
-    while (c->produced.load() <= c->consumed.load()) {
+    while (r.produced.load() <= r.consumed.load()) {
+        if (r.aborted.load()) return fail("recording aborted: %s", r.why().c_str());
         if (std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - t0).count() >= timeout_ms) {
             *tt = -1; *frame = nullptr;
             g_err = "timeout";
@@ -1360,17 +1381,104 @@ int phb_record_next(phb_ctx *c, const double **frame, int64_t *tt, int32_t timeo
         }
         std::this_thread::sleep_for(std::chrono::microseconds(100));
     }
-    const int s = (int)(c->consumed.load() % c->slots);
+    const int s = (int)(r.consumed.load() % r.slots);
     cudaSetDevice(c->device);
-    CU(cudaEventSynchronize(c->slot_ev[s]));
-    *frame = c->ring + (long long)s * c->frame_doubles;
-    *tt = c->slot_tt[s];
-    c->consumed.fetch_add(1);
+    CU(cudaEventSynchronize(r.slot_ev[s]));
+    *frame = r.host + (long long)s * r.frame_doubles;
+    *tt = r.slot_tt[s];
+    r.consumed.fetch_add(1);
     return 0;
 }
 int phb_record_release(phb_ctx *c) {
-    if (!c || !c->ring) return fail("recording not enabled");
-    if (c->released.load() < c->consumed.load()) c->released.fetch_add(1);
+    if (!c || !c->rec.host) return fail("recording not enabled");
+    if (c->rec.released.load() < c->rec.consumed.load()) c->rec.released.fetch_add(1);
+    return 0;
+}
+int phb_record_abort(phb_ctx *c, const char *why) {
+    if (!c) return fail("null context");
+    c->rec.abort(why && *why ? why : "aborted by the consumer");
+    return 0;
+}
+int phb_record_timeout(phb_ctx *c, int32_t timeout_ms) {
+    if (!c) return fail("null context");
+    c->rec.timeout_ms.store(timeout_ms > 0 ? timeout_ms : 1);
+    return 0;
+}
+int phb_cancel(phb_ctx *c) {
+    if (!c) return fail("null context");
+    c->cancel.store(1);
+    return 0;
+}
+
+// ---- native writer ---------------------------------------------------------------------------------
+static int writer_setup(NativeWriter &w, RecRing &r, int fd, int32_t ncomp, const int64_t *base, const int64_t *bytes, int64_t stride,
+                        int64_t frames) {
+    if (fd < 0 || ncomp < 1 || ncomp > 3 || !base || !bytes || frames < 0) return fail("bad writer arguments");
+    long long off = 0;
+    for (int q = 0; q < ncomp; ++q) {
+        if (bytes[q] <= 0 || base[q] < 0) return fail("bad extent for component %d", q);
+        w.base[q] = base[q]; w.bytes[q] = bytes[q]; w.off[q] = off;
+        off += bytes[q];
+    }
+    if (off != r.frame_doubles * 8) return fail("components add up to %lld bytes, a ring frame has %lld", off, r.frame_doubles * 8);
+    w.fd = fd; w.ncomp = ncomp; w.stride = stride; w.frames = frames;
+    w.wait_us.store(0); w.write_us.store(0);
+    return 0;
+}
+int phb_writer_start(phb_ctx *c, int32_t fd, int32_t ncomp, const int64_t *base, const int64_t *bytes, int64_t stride,
+                     int64_t frames, int32_t nthreads) {
+    if (!c || !c->rec.host) return fail("recording not enabled");
+    if (c->wr.started) return fail("writer already started");
+    if (c->rec.produced.load() != 0) return fail("frames were recorded before the writer started");
+    OK(writer_setup(c->wr, c->rec, fd, ncomp, base, bytes, stride, frames));
+    return c->wr.start(&c->rec, nthreads > 0 ? nthreads : 4);
+}
+int phb_writer_finish(phb_ctx *c, int32_t timeout_ms, int64_t *written, double *wait_s, double *write_s) {
+    if (!c) return fail("null context");
+    const bool ok = c->wr.finish(timeout_ms > 0 ? timeout_ms : 300000);      // reference: join(300), base_solver.py:89-92,274
+    if (written) *written = c->wr.written.load();
+    if (wait_s) *wait_s = 1e-6 * (double)c->wr.wait_us.load();
+    if (write_s) *write_s = 1e-6 * (double)c->wr.write_us.load();
+    if (!ok) return fail("writer threads did not finish within %d ms", timeout_ms);
+    if (c->rec.aborted.load()) return fail("%s", c->rec.why().c_str());
+    return 0;
+}
+// CPU-only exercise of the ring + writer threads (tests): a host thread produces `frames` frames of `frame_doubles`
+// doubles, frame f element q = f * 1e6 + q, through a `slots`-deep ring; the writer threads store them at
+// base[c] + f * stride.  abort_at >= 0: the producer stops there as if cancelled.  No CUDA call is made.
+int phb_writer_selftest(int32_t fd, int32_t ncomp, const int64_t *base, const int64_t *bytes, int64_t stride, int64_t frames,
+                        int32_t slots, int32_t nthreads, int32_t timeout_ms, int64_t *written) {
+    if (slots < 1 || frames < 0) return fail("bad arguments");
+    RecRing r;
+    long long fb = 0;
+    for (int q = 0; q < ncomp && q < 3; ++q) fb += bytes ? bytes[q] : 0;
+    if (fb <= 0 || fb % 8) return fail("bad frame size");
+    r.frame_doubles = fb / 8;
+    r.slots = slots;
+    r.timeout_ms.store(timeout_ms > 0 ? timeout_ms : 1000);
+    std::vector<double> host((size_t)(r.frame_doubles * slots));
+    r.host = host.data();
+    r.slot_tt.assign(slots, -1);
+    NativeWriter w;
+    OK(writer_setup(w, r, fd, ncomp, base, bytes, stride, frames));
+    w.start(&r, nthreads > 0 ? nthreads : 2);
+    int rc = 0;
+    for (long long f = 0; f < frames && !rc; ++f) {
+        const int wf = r.wait_free();
+        if (wf == 1) rc = fail("recording aborted: %s", r.why().c_str());
+        else if (wf) rc = fail("recorder ring full for %d ms", r.timeout_ms.load());
+        else {
+            double *slot = r.host + (f % slots) * r.frame_doubles;
+            for (long long q = 0; q < r.frame_doubles; ++q) slot[q] = (double)f * 1e6 + (double)q;
+            r.slot_tt[(size_t)(f % slots)] = f;
+            r.produced.fetch_add(1);
+        }
+    }
+    const bool ok = w.finish(timeout_ms > 0 ? timeout_ms : 1000);
+    if (written) *written = w.written.load();
+    if (rc) return rc;
+    if (!ok) return fail("writer threads did not finish");
+    if (r.aborted.load()) return fail("%s", r.why().c_str());
     return 0;
 }
 

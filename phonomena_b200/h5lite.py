@@ -129,11 +129,12 @@ class H5Writer:
         except OSError:
             pass
 
-    def preallocate(self, nbytes):
-        """Reserve file space for `nbytes` more data now (posix_fallocate): on tmpfs / page cache the pages are then
-        allocated outside the stepping loop and the frame writes are plain copies.  Best effort."""
+    def preallocate(self, nbytes, start=None):
+        """Reserve file space for `nbytes` of data now (posix_fallocate), from `start` (default: the current end): on
+        tmpfs / page cache the pages are then allocated outside the stepping loop and the frame writes are plain
+        copies.  Best effort."""
         try:
-            os.posix_fallocate(self.fd, self._end, int(nbytes))
+            os.posix_fallocate(self.fd, self._end if start is None else int(start), int(nbytes))
         except (OSError, AttributeError):
             pass
 
@@ -165,6 +166,34 @@ class H5Writer:
 
     def pwrite(self, raw, pos):
         self._pwrite(raw, pos)
+
+    def reserve_frames(self, datasets, frames):
+        """Reserve the extents of frames 0 .. frames-1 of several chunked datasets at once, interleaved frame by
+        frame (frame t of every dataset, then frame t+1, ...) so that a run appends to the file sequentially.
+        Returns (base, stride): frame t of datasets[c] lives at base[c] + t * stride.  The native writer threads
+        (phb_writer_start) fill them; call keep_frames(n) before close() if fewer were written."""
+        with self._lock:
+            pos = self._end + (-self._end % 8)
+            stride = sum(d.frame_bytes for d in datasets)
+            base, off = [], 0
+            for d in datasets:
+                if d.addr:
+                    raise ValueError("dataset %s already has frames" % d.name)
+                if frames > d.shape[-1]:
+                    raise ValueError("%d frames for dataset %s of %d" % (frames, d.name, d.shape[-1]))
+                base.append(pos + off)
+                for t in range(frames):
+                    d.addr[t] = pos + off + t * stride
+                off += d.frame_bytes
+            self._end = pos + stride * frames
+        return base, stride
+
+    def keep_frames(self, n):
+        """Forget the reserved frames with index >= n (a cancelled run wrote fewer than it reserved): readers
+        then see them as never written (fill value) instead of whatever the extent holds."""
+        for d in self._chunked:
+            for t in [t for t in d.addr if t >= n]:
+                del d.addr[t]
 
     # -- chunk B-tree (v1, node type 1) --------------------------------------------------------
     def _chunk_btree(self, d):

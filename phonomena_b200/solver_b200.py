@@ -74,11 +74,16 @@ class Writer:
 
     surface mode: datasets ux (Nx-1,Ny,1,frames), uy (Nx,Ny-1,1,frames), uz (Nx,Ny,1,frames),
     chunk = one frame, so `u[:, :, 0, t]` of the consumers (h5py2gif.py:24,44; analysis.py:59-66)
-    works unchanged.  full mode: the reference's full 4-D datasets."""
+    works unchanged.  full mode: the reference's full 4-D datasets.
 
-    WRITE_THREADS = 8      # surface mode: positional writes in flight
-    PIECES = 2             # pieces per recorded component and frame
-    PARALLEL_MIN_BYTES = 1 << 19
+    This class owns the file and its layout (h5lite); the frames themselves never pass through Python:
+    the chunk extents of all frames are reserved up front and native threads inside libphb200.so
+    (phb_writer_start, csrc/rec_ring.h) pwrite() every recorded frame from the pinned ring straight to
+    its extent.  A write error (ENOSPC ...) aborts the recording, which makes the stepping call fail with
+    the errno text -- the run loop cannot hang on a dead writer (reference: queue.get(timeout=120),
+    join(300), base_solver.py:89-92,148,274)."""
+
+    WRITE_THREADS = 4      # native threads, each writes whole frames
     PREALLOCATE_MAX_BYTES = 2 << 30
 
     def __init__(self, path, engine, meta, frames, mode, record_every, ring=True, fields=("ux", "uy", "uz")):
@@ -100,62 +105,27 @@ class Writer:
         # The static datasets (density alone is Nx*Ny*Nz doubles) are pushed out now, in init(), like the reference's
         # Writer.init (base_solver.py:105-133): otherwise the kernel's dirty-page writeback of them throttles the
         # frame appends of the stepping loop.
-        total = frames * sum(d.frame_bytes + 8 for d in self.ds.values())
-        if self.ring and total <= self.PREALLOCATE_MAX_BYTES:
-            self.h5.preallocate(total)
+        self._layout = None
+        if self.ring and frames > 0:
+            start = self.h5._end
+            base, stride = self.h5.reserve_frames(list(self.ds.values()), frames)
+            self._layout = (base, [d.frame_bytes for d in self.ds.values()], stride)
+            if stride * frames <= self.PREALLOCATE_MAX_BYTES:
+                self.h5.preallocate(stride * frames, start)
         self.h5.settle()
         self.written = 0
-        self.wait_seconds = self.write_seconds = 0.0     # writer thread: waiting for frames / writing them
+        self.wait_seconds = self.write_seconds = 0.0     # writer threads: waiting for frames / writing them
         self.error = None
-        self._stop = threading.Event()
-        self.thread = None
+        self.started = self.finished = False
 
-    # consumer thread of the pinned ring (surface frames, or whole arrays when they fit a ring)
     def start(self):
-        if not self.ring:
+        if self._layout is None:
             return
-        self.thread = threading.Thread(target=self._drain, name="phb-writer", daemon=True)
-        self.thread.start()
+        base, nbytes, stride = self._layout
+        self.e.writer_start(self.h5.fd, base, nbytes, stride, self.frames, self.WRITE_THREADS)
+        self.started = True
 
-    def _drain(self):
-        # one positional write per recorded component, in parallel (os.pwrite releases the GIL): a single
-        # thread copying 6 MB frames into the page cache is slower than the GPU produces them at 512^3
-        from concurrent.futures import ThreadPoolExecutor
-        try:
-            with ThreadPoolExecutor(max_workers=self.WRITE_THREADS, thread_name_prefix="phb-h5") as pool:
-                while self.written < self.frames:
-                    t0 = time.perf_counter()
-                    got = self.e.record_next(timeout_ms=200)
-                    t1 = time.perf_counter()
-                    self.wait_seconds += t1 - t0
-                    if got is None:
-                        if self._stop.is_set():
-                            break
-                        continue
-                    _tt, views = got
-                    jobs = []
-                    for name, a in views.items():
-                        d = self.ds[name]
-                        mv = memoryview(np.ascontiguousarray(a, dtype="<f8").reshape(-1)).cast("B")
-                        if mv.nbytes != d.frame_bytes:
-                            raise ValueError("frame of %d bytes for dataset %s, expected %d" % (mv.nbytes, name, d.frame_bytes))
-                        pos = self.h5.reserve_frame(d, self.written)
-                        if mv.nbytes < self.PARALLEL_MIN_BYTES:       # small grids: one write, no hand-off
-                            self.h5.pwrite(mv, pos)
-                            continue
-                        piece = -(-mv.nbytes // self.PIECES)
-                        piece += -piece % 4096            # page-aligned pieces
-                        for o in range(0, mv.nbytes, piece):
-                            jobs.append(pool.submit(self.h5.pwrite, mv[o:o + piece], pos + o))
-                    for jb in jobs:
-                        jb.result()
-                    self.e.record_release()
-                    self.written += 1
-                    self.write_seconds += time.perf_counter() - t1
-        except Exception as exc:       # surfaced by Solver.run
-            self.error = exc
-
-    # full mode: called synchronously by the run loop
+    # full mode without a ring: called synchronously by the run loop
     def put_full(self, fields):
         for name, a in zip(("ux", "uy", "uz"), fields):
             if name in self.ds:
@@ -163,15 +133,33 @@ class Writer:
         self.written += 1
 
     def finish(self, timeout=300.0):
-        if self.thread is not None:
-            self._stop.set()
-            self.thread.join(timeout)
-            if self.thread.is_alive():
-                raise TimeoutError("writer thread did not finish")
+        """Drain, join the native threads, close the file.  Raises what the writer threads hit."""
+        if self.finished:
+            return
+        self.finished = True
+        if self.started:
+            try:
+                self.e.writer_finish(int(timeout * 1000))
+            except Exception as exc:
+                self.error = exc
+            self.written, self.wait_seconds, self.write_seconds = getattr(self.e, "writer_stats", (0, 0.0, 0.0))
+            self.h5.keep_frames(self.written)
         self.h5.attrs["frames_written"] = int(self.written)
         self.h5.close()
         if self.error is not None:
             raise self.error
+
+    def abort(self, why="writer abandoned"):
+        """Stop without raising (init() called again, or the solver is being destroyed): the file is closed with the
+        frames written so far, the native threads are joined before the engine goes away."""
+        if self.finished:
+            return
+        if self.started:
+            self.e.record_abort(why)
+        try:
+            self.finish(timeout=5.0)
+        except Exception:
+            pass
 
 
 class Solver:
@@ -196,7 +184,9 @@ class Solver:
     def init(self, grid, material, steps):
         """Prepare a run: copies what it needs (the caller's objects are not mutated and may be
         freed), rebuilds the mesh like the reference does, uploads everything, zeroes the fields."""
-        self._close_engine()
+        self._close_engine()       # also stops a writer left over from a previous init() (base_solver.py:209-211)
+        self._ran = False
+        t_init = time.time()
         c = self.cfg
         self.t = int(copy.deepcopy(steps))
         logger.info("Initializing %s with settings: %s", self.name, c)
@@ -298,12 +288,18 @@ class Solver:
             self.writer = Writer(path, e, meta, frames, rec_mode, int(c["record_every"]), ring=self._full_ring, fields=fields)
             self.writer.start()
         self._rec_mode = rec_mode
+        self.init_seconds = time.time() - t_init
 
     # ------------------------------------------------------------------------------------
     def run(self, *args, **kwargs):
         signals = kwargs.get("signals") or _DummySignals()
         if self.engine is None:
             raise RuntimeError("init() must be called before run()")
+        if getattr(self, "_ran", False):
+            # the reference's second run() dies on its finished writer ("Process not started" / closed queue); here the
+            # recorder would wait for a consumer that no longer exists -- refuse instead
+            raise RuntimeError("run() was already called for this init(); call init() again")
+        self._ran = True
         e, c = self.engine, self.cfg
         signals.status.emit("Solver starting..")
         self.running.set()
@@ -326,15 +322,18 @@ class Solver:
                 # the source samples of this chunk: evaluated on the host with the reference's
                 # expression and copied to the device inside the loop (base_solver.py:251)
                 e.set_source_table(hm.source_table(self._wave, n, self.dt, self._wave_args, start=done))
-                e.run(n)
+                try:
+                    e.run(n)
+                except _lib.PhbCancelled:       # cancel() reached the library between two steps of this chunk
+                    done = e.steps_done
+                    self.logger.warning("Simulation cancelled.")
+                    break
                 done += n
                 if self._rec_mode == "full" and not self._full_ring:
                     if done % every == 0:
                         self.writer.put_full(e.get_fields())
                 elif self._rec_mode not in ("surface", "full"):
                     e.sync()
-                if self.writer is not None and self.writer.error is not None:
-                    raise self.writer.error
                 if progress < 99:
                     progress = min(99, int((done / self.t) * 100))
                     signals.progress.emit(progress)
@@ -358,7 +357,7 @@ class Solver:
         cells = e.nx * e.ny * e.nz
         self.stats = {"steps": done, "seconds": etime, "gcells_per_s": cells * done / etime / 1e9 if etime > 0 else 0.0,
                       "launches": e.launch_count - l0, "kernel": e.info()["kernel"],
-                      "loop_seconds": getattr(self, "_loop_seconds", 0.0),
+                      "loop_seconds": getattr(self, "_loop_seconds", 0.0), "init_seconds": getattr(self, "init_seconds", 0.0),
                       "writer_finish_seconds": getattr(self, "_finish_seconds", 0.0),
                       "writer_wait_seconds": self.writer.wait_seconds if self.writer is not None else 0.0,
                       "writer_write_seconds": self.writer.write_seconds if self.writer is not None else 0.0}
@@ -368,6 +367,9 @@ class Solver:
     def cancel(self):
         if self.running.is_set():
             self.running.clear()
+            e = self.engine
+            if e is not None:
+                e.cancel()      # the chunk in flight stops after its current step (also when it waits for the recorder ring)
 
     def allgather(self, obj):
         """All-gather a small Python object over the ranks (multi-GPU runs); see broadcast()."""
@@ -427,6 +429,9 @@ class Solver:
         return self.engine.get_fields()
 
     def _close_engine(self):
+        if self.writer is not None:
+            self.writer.abort("solver re-initialised or closed")     # joins the native writer threads, closes the file
+            self.writer = None
         if self.engine is not None:
             self.engine.close()
             self.engine = None

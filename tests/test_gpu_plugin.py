@@ -235,3 +235,77 @@ def test_plugin_record_fields_subset(tmp_path):
     with pytest.raises(ValueError):
         s = make_solver(d, tmp_path, record_fields=[])
         s.init(*fake_from_golden(d), 10)
+
+
+# ---- the recorder cannot hang run() (reference: queue.get(timeout=120), join(300), base_solver.py:89-92,148,274) ----
+def test_plugin_writer_failure_raises_instead_of_hanging(tmp_path):
+    """The writer threads hit a write error on the first frame (their descriptor is swapped for a read-only one):
+    Solver.run() must raise with the errno text within about a second, not wait for a free ring slot forever."""
+    import os
+    from phonomena_b200 import _lib
+    d = H.load_golden("crystal_48x32x12")
+    s = make_solver(d, tmp_path, record="surface", chunk_steps=20)
+    s.init(*fake_from_golden(d), 400)            # 400 frames >> 32 ring slots
+    ro = os.open(os.devnull, os.O_RDONLY)
+    keep = os.dup(s.writer.h5.fd)
+    os.dup2(ro, s.writer.h5.fd)                  # native pwrite -> EBADF
+    t0 = time.time()
+    with pytest.raises(_lib.PhbError, match="pwrite"):
+        s.run()
+    assert time.time() - t0 < 3.0
+    os.dup2(keep, s.writer.h5.fd)
+    os.close(keep)
+    os.close(ro)
+    with pytest.raises(RuntimeError, match="init"):
+        s.run()                                  # a second run() without init() is refused, not hung
+
+
+def test_recorder_full_ring_times_out_and_cancel_breaks_in():
+    """No consumer at all: phb_run fails after the configured wait; phb_cancel from another thread ends a wait in progress."""
+    from phonomena_b200 import _lib
+    d = H.load_golden("crystal_48x32x12")
+    with H.engine_from_golden(d, record_mask=_lib.REC_UZ, ring_slots=4) as e:
+        e.record_timeout(300)
+        t0 = time.time()
+        with pytest.raises(_lib.PhbError, match="ring full"):
+            e.run(50)
+        assert 0.25 < time.time() - t0 < 2.0 and e.steps_done == 5      # 4 frames fit, the 5th step's frame does not
+    with H.engine_from_golden(d, record_mask=_lib.REC_UZ, ring_slots=4) as e:
+        e.record_timeout(60000)
+        threading.Timer(0.3, e.cancel).start()
+        t0 = time.time()
+        with pytest.raises(_lib.PhbCancelled):
+            e.run(50)
+        assert time.time() - t0 < 2.0
+        # the consumer API still drains what was recorded
+        tt, views = e.record_next(timeout_ms=1000)
+        assert tt == 0 and views["uz"].shape == (48, 32)
+        e.record_release()
+        e.record_abort("test")
+        with pytest.raises(_lib.PhbError, match="aborted"):
+            e.run(1)
+
+
+def test_plugin_reinit_without_run_and_cancel_latency(tmp_path):
+    """init() twice with no run() in between: the first writer is stopped and its file closed before the engine it
+    reads from is destroyed (was a use-after-free).  cancel() stops a long chunk within a step, not a chunk."""
+    from phonomena_b200.h5lite import H5Reader
+    d = H.load_golden("crystal_48x32x12")
+    s = make_solver(d, tmp_path, record="surface")
+    s.file = str(tmp_path / "first.h5")
+    s.init(*fake_from_golden(d), 30)
+    first = s.file
+    s.file = str(tmp_path / "second.h5")
+    s.init(*fake_from_golden(d), 30)
+    assert H5Reader(first).attrs["frames_written"] == 0
+    s.run()
+    assert H5Reader(s.file).attrs["frames_written"] == 30
+    s2 = make_solver(d, tmp_path, write_mode="off", chunk_steps=10_000_000)
+    s2.init(*fake_from_golden(d), 10_000_000)
+    th = threading.Thread(target=s2.run)
+    th.start()
+    time.sleep(0.3)
+    t0 = time.time()
+    s2.cancel()
+    th.join(5)
+    assert not th.is_alive() and time.time() - t0 < 1.0 and 0 < s2.stats["steps"] < 10_000_000

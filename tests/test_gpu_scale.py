@@ -107,3 +107,67 @@ def test_config2_256cube_1000_steps_fp32_and_fast_within_tolerance():
     assert all(np.isfinite(a).all() for a in out["exact"]) and float(np.abs(out["exact"][2]).max()) > 0.5
     assert H.rel_l2(out["fast"], out["exact"]) <= 1e-12
     assert H.rel_l2(out["f32"], out["exact"]) <= 1e-5
+
+
+def test_config3_512cube_vs_c_oracle():
+    """BASELINE config #3 itself (the grid bench.py times): 512^3 phononic crystal, 256 Au cylinders, left-wall sin
+    source -- the CUDA path against the C/OpenMP oracle (pinned bit-for-bit to the reference) for 3 steps.
+    The id map the oracle steps with is the ORACLE's own (Grid.inclusionIndices restated), and the device's map must
+    equal it.  Bitwise in EXACT mode, <= 1e-12 FAST, <= 1e-5 fp32."""
+    from oracle import fdtd_numpy as onp
+    from phonomena_b200.workloads import crystal_case
+    steps = 3
+    case = crystal_case(512, 512, 512)
+    assert len(case.targets) == 256
+    ids = onp.material_id_map(case.x, case.y, case.z, onp.make_targets(case.targets.tolist()))
+    assert 0.18 < ids.mean() < 0.20                     # 18.85 % secondary fill (SURVEY 8d)
+    ref = _c_oracle(case, ids, steps)
+    assert sum(float(np.abs(a).sum()) for a in ref) > 0
+    with case.make_engine(steps=steps, dtype="f64", arith="exact") as e:
+        assert np.array_equal(e.get_material_ids(), ids)
+        e.run(steps)
+        got = e.get_fields()
+        assert e.info()["kernel"] == "march_tma"
+    for a, b, n in zip(got, ref, "xyz"):
+        assert np.array_equal(a, b), ("u" + n, float(np.abs(a - b).max()))
+    del got
+    with case.make_engine(steps=steps, dtype="f64", arith="fast") as e:
+        e.run(steps)
+        assert H.rel_l2(e.get_fields(), ref) <= 1e-12
+    with case.make_engine(steps=steps, dtype="f32", arith="fast") as e:
+        e.run(steps)
+        assert H.rel_l2(e.get_fields(), ref) <= 1e-5
+
+
+def test_material_id_map_at_scale_nonuniform_mesh():
+    """Device-side inclusion fill against the oracle's restatement of Grid.inclusionIndices / Material.setConstants
+    (grid.py:158-175, material.py:55-63) on a 272 x 200 x 168 mesh that is NON-uniform in x and y, with cylinders whose
+    float32 centres / radii put mesh lines exactly on and next to the `R < r` edge, partial depths (z re-binding
+    quirk, App. A.7) and overlaps -- and through a 3-slab decomposition (each slab generates only its planes)."""
+    from oracle import fdtd_numpy as onp
+    from phonomena_b200 import _lib
+    rng = np.random.default_rng(5)
+    nx, ny, nz = 272, 200, 168
+    x = np.concatenate([[0.0], np.cumsum(rng.choice([0.3076921701431274, 0.5, 1.0, 1.4000000000000004], nx - 1))])
+    y = np.concatenate([[0.0], np.cumsum(rng.choice([0.25, 0.75, 1.0, 1.1], ny - 1))])
+    z = 0.5 * np.arange(nz, dtype=np.float64)           # dz = 0.5: after the first inclusion `z` means INDICES (grid.py:173)
+    rows = []
+    for _ in range(70):
+        i, j = int(rng.integers(10, nx - 10)), int(rng.integers(10, ny - 10))
+        r = float(rng.choice([2.0, 3.3, 5.0, 7.5]))
+        # centre on a mesh line, radius an exact sum of spacings for some: edge cells decided by float32 rounding
+        cx = x[i] if rng.random() < 0.5 else x[i] + 0.37
+        rows.append((cx, y[j], float(rng.choice([83.5, 120.0, 60.0, 40.5, 7.0])), r))
+    rows.append((x[100], y[100], 83.5, float(x[104] - x[100])))        # R == r exactly on mesh lines (strict <)
+    rows.sort(key=lambda t: -t[2])                      # the z filter is cumulative: deepest first keeps the profiles distinct
+    tg = onp.make_targets(rows)
+    want = onp.material_id_map(x, y, z, tg)
+    assert 0.005 < want.mean() < 0.6 and len({int(v) for v in want.sum(axis=2).reshape(-1)}) > 3      # several depth profiles
+    t4 = np.array([[t["x"], t["y"], t["z"], t["r"]] for t in tg], np.float32)
+    with _lib.Engine(nx, ny, nz, 1e-6) as e:
+        e.gen_material_ids(t4, x, y, z)
+        assert np.array_equal(e.get_material_ids(), want)
+    for x0, nxl in ((0, 90), (90, 91), (181, 91)):
+        with _lib.Engine(nx, ny, nz, 1e-6, x0=x0, nxl=nxl) as e:
+            e.gen_material_ids(t4, x, y, z)
+            assert np.array_equal(e.get_material_ids(), want[x0:x0 + nxl]), x0

@@ -120,15 +120,21 @@ def test_bench_reference_arm_contract_line():
     import json
     import subprocess
     import sys
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
-                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "3", "--warmup", "1",
+                        "--quick-reference"], capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-2000:]
     line = json.loads(r.stdout.strip().splitlines()[-1])
     for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
               "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert k in line, k
     assert line["impl"] == "reference" and line["metric"] == "Gcell-updates/s" and line["unit"] == "Gcell/s"
-    assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    from oracle import refshim
+    # the unmodified reference when a copy is present (build container: /root/reference; GPU box: oracle/_ref), else the port
+    assert line["cpu_baseline"]["kind"] == ("reference" if refshim.available() else "port")
+    assert line["value"] > 0 and line["cpu_baseline"]["cores"] >= 1 and line["host"]["cpu_model"]
+    if refshim.available():
+        runs = line["extra"]["runs"]["128"]
+        assert runs["solver_threading"]["uz_norm"] == runs["solver_default"]["uz_norm"] > 0      # the two reference solvers agree bit for bit
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"] and "workload" in line["config"]
 
 
@@ -206,58 +212,114 @@ def test_h5lite_positional_frames_from_threads(tmp_path):
 
 
 class _FakeRingEngine:
-    """Stands in for _lib.Engine on the CPU: hands the plugin's Writer a scripted sequence of recorder frames
-    (the real one returns views into the pinned ring; record_next / record_release keep the same contract)."""
+    """Stands in for _lib.Engine on the CPU: writer_start / writer_finish run the library's OWN ring + writer threads
+    (phb_writer_selftest: a host producer pushes synthetic frames, element q of frame f = f * 1e6 + q, through the ring
+    the device would fill) against the extents the plugin's Writer reserved."""
 
-    def __init__(self, nx, ny, nz, frames, fields, full, rng):
+    def __init__(self, nx, ny, nz, produce, fail_fd=False):
         self.nx, self.ny, self.nz, self.x0, self.nxl = nx, ny, nz, 0, nx
-        shp = {"ux": (nx - 1, ny), "uy": (nx, ny - 1), "uz": (nx, ny)}
-        zext = {"ux": nz, "uy": nz, "uz": nz - 1}
-        self.data = [{k: rng.standard_normal(shp[k] + ((zext[k],) if full else ())) for k in fields} for _ in range(frames)]
-        self.next, self.held, self.released = 0, False, 0
+        self.produce, self.fail_fd, self.args, self.aborted = produce, fail_fd, None, None
 
     def planes(self, comp):
         return self.nx - 1 if comp == 0 else self.nx
 
-    def record_next(self, timeout_ms=0):
-        assert not self.held, "record_next called again before record_release"
-        if self.next >= len(self.data):
-            return None
-        self.held = True
-        self.next += 1
-        return self.next - 1, self.data[self.next - 1]
+    def writer_start(self, fd, base, nbytes, stride, frames, nthreads=4):
+        self.args = (fd, list(base), list(nbytes), stride, frames, nthreads)
 
-    def record_release(self):
-        assert self.held
-        self.held = False
-        self.released += 1
+    def writer_finish(self, timeout_ms=300000):
+        from phonomena_b200 import _lib
+        fd, base, nbytes, stride, frames, nthreads = self.args
+        assert self.produce <= frames
+        if self.fail_fd:
+            fd = os.open(os.devnull, os.O_RDONLY)       # pwrite on a read-only descriptor: EBADF
+        try:
+            n = _lib.writer_selftest(fd, base, nbytes, stride, self.produce, slots=3, nthreads=nthreads, timeout_ms=2000)
+        except _lib.PhbError:
+            self.writer_stats = (0, 0.0, 0.0)
+            raise
+        finally:
+            if self.fail_fd:
+                os.close(fd)
+        self.writer_stats = (n, 0.0, 0.0)
+        return self.writer_stats
+
+    def record_abort(self, why=""):
+        self.aborted = why
 
 
-@pytest.mark.parametrize("full,fields,parallel", [(False, ("ux", "uy", "uz"), True), (False, ("uz",), False),
-                                                   (True, ("ux", "uy", "uz"), True), (True, ("uy", "uz"), False)])
-def test_plugin_writer_thread_on_scripted_frames(tmp_path, full, fields, parallel):
-    """The plugin's Writer (ring consumer thread, preallocation, piecewise parallel positional writes above
-    PARALLEL_MIN_BYTES, one write below it, record_fields subsets) against a scripted frame source: the file holds
-    every frame in order, with the reference's dataset shapes (z extent 1 in surface mode)."""
+@pytest.mark.parametrize("full,fields,produce", [(False, ("ux", "uy", "uz"), 7), (False, ("uz",), 7),
+                                                  (True, ("ux", "uy", "uz"), 7), (True, ("uy", "uz"), 4)])
+def test_plugin_writer_native_threads_on_synthetic_frames(tmp_path, full, fields, produce):
+    """The plugin's Writer (file layout, up-front reservation of every frame's extent, preallocation, record_fields
+    subsets) + the library's native writer threads draining a ring: the file holds every produced frame in order, with
+    the reference's dataset shapes (z extent 1 in surface mode); a run that stops early (cancel) leaves the missing
+    frames unwritten, not garbage."""
     from phonomena_b200.h5lite import H5Reader
     from phonomena_b200.solver_b200 import Writer
     rng = np.random.default_rng(11)
     nx, ny, nz, frames = 9, 8, 5, 7
-    eng = _FakeRingEngine(nx, ny, nz, frames, fields, full, rng)
+    eng = _FakeRingEngine(nx, ny, nz, produce)
     meta = {"attrs": {"dt": 0.25, "x": np.arange(nx, dtype=float)}, "density": rng.standard_normal((nx, ny, nz)), "elasticity": None}
     w = Writer(str(tmp_path / "w.h5"), eng, meta, frames, "full" if full else "surface", 1, ring=True, fields=fields)
-    if parallel:
-        w.PARALLEL_MIN_BYTES = 64          # force the multi-piece path on these tiny frames
     w.start()
     w.finish()
-    assert w.error is None and w.written == frames and eng.released == frames
+    w.finish()                                  # idempotent
+    assert w.error is None and w.written == produce
+    shp = {"ux": (nx - 1, ny), "uy": (nx, ny - 1), "uz": (nx, ny)}
+    zext = {"ux": nz, "uy": nz, "uz": nz - 1}
     r = H5Reader(w.path)
     assert sorted(k for k in r.datasets if k.startswith("u")) == sorted(fields)
-    assert r.attrs["frames_written"] == frames and r.attrs["record"] == ("full" if full else "surface")
-    for k in fields:
-        exp_shape = eng.data[0][k].shape + (() if full else (1,)) + (frames,)
-        assert r.shape(k) == exp_shape, (k, r.shape(k), exp_shape)
-        for t in range(frames):
-            got = r.read(k, frame=t)
-            assert np.array_equal(got if full else got[..., 0], eng.data[t][k]), (k, t)
+    assert r.attrs["frames_written"] == produce and r.attrs["record"] == ("full" if full else "surface")
+    q0 = 0
+    for k in fields:                            # ring order = ux, uy, uz as selected
+        fshape = shp[k] + ((zext[k],) if full else (1,))
+        n = int(np.prod(fshape))
+        assert r.shape(k) == fshape + (frames,), (k, r.shape(k))
+        for t in range(produce):
+            exp = (t * 1e6 + q0 + np.arange(n, dtype=np.float64)).reshape(fshape)
+            assert np.array_equal(r.read(k, frame=t), exp), (k, t)
+        whole = r.read(k)
+        assert not whole[..., produce:].any()   # frames never written read as zeros
+        q0 += n
     assert np.array_equal(r.read("density"), meta["density"])
+
+
+def test_plugin_writer_error_surfaces_and_abort_is_quiet(tmp_path):
+    """A write error inside the native threads (here EBADF) comes back from finish() as an exception carrying the errno
+    text, and the file is still closed as a valid (empty) recording; abort() -- what init()-again and __del__ use --
+    never raises."""
+    from phonomena_b200 import _lib
+    from phonomena_b200.h5lite import H5Reader
+    from phonomena_b200.solver_b200 import Writer
+    meta = {"attrs": {"dt": 0.25}, "density": np.zeros((6, 5, 4)), "elasticity": None}
+    eng = _FakeRingEngine(6, 5, 4, 5, fail_fd=True)
+    w = Writer(str(tmp_path / "e.h5"), eng, meta, 5, "surface", 1, fields=("uz",))
+    w.start()
+    with pytest.raises(_lib.PhbError, match="pwrite"):
+        w.finish()
+    r = H5Reader(w.path)
+    assert r.attrs["frames_written"] == 0 and r.shape("uz") == (6, 5, 1, 5)
+    eng2 = _FakeRingEngine(6, 5, 4, 5, fail_fd=True)
+    w2 = Writer(str(tmp_path / "a.h5"), eng2, meta, 5, "surface", 1, fields=("uz",))
+    w2.start()
+    w2.abort("re-init")
+    assert eng2.aborted == "re-init" and w2.finished and H5Reader(w2.path).attrs["frames_written"] == 0
+
+
+def test_native_ring_flow_control_and_threads(tmp_path):
+    """phb_writer_selftest directly: more frames than ring slots (the producer has to wait for in-order releases), 1..4
+    writer threads, interleaved component extents."""
+    from phonomena_b200 import _lib
+    for nthreads in (1, 2, 4):
+        p = str(tmp_path / ("ring%d.bin" % nthreads))
+        fd = os.open(p, os.O_RDWR | os.O_CREAT | os.O_TRUNC, 0o644)
+        nb = [24 * 8, 40 * 8]
+        stride, frames = sum(nb) + 64, 50
+        base = [128, 128 + nb[0]]
+        assert _lib.writer_selftest(fd, base, nb, stride, frames, slots=3, nthreads=nthreads) == frames
+        os.close(fd)
+        raw = np.fromfile(p, dtype="<f8")
+        for f in (0, 1, 17, 49):
+            a = raw[(base[0] + f * stride) // 8:][:24]
+            b = raw[(base[1] + f * stride) // 8:][:40]
+            assert np.array_equal(a, f * 1e6 + np.arange(24)) and np.array_equal(b, f * 1e6 + 24 + np.arange(40)), (nthreads, f)
