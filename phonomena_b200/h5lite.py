@@ -234,6 +234,16 @@ class H5Writer:
     def close(self):
         if self.closed:
             return
+        try:
+            self._write_metadata()
+        finally:            # the descriptor is released whatever the metadata writes hit (ENOSPC, EBADF, ...)
+            self.closed = True
+            try:
+                os.close(self.fd)
+            except OSError:
+                pass
+
+    def _write_metadata(self):
         fill_early = struct.pack("<BBBB", 2, 1, 2, 0)           # fill value v2: alloc early, write "if set", undefined
         fill_incr = struct.pack("<BBBB", 2, 3, 2, 0)            # alloc incremental (chunked)
         objects = {}                                            # name -> object header address
@@ -284,8 +294,6 @@ class H5Writer:
             os.ftruncate(self.fd, eof)          # drop preallocated space that was not used
         except OSError:
             pass
-        os.close(self.fd)
-        self.closed = True
 
     def __enter__(self):
         return self
@@ -371,6 +379,37 @@ class H5Reader:
         for mtype, data in self._messages(self.datasets[name]):
             if mtype == 0x0001:
                 return struct.unpack_from("<%dQ" % data[1], data, 8)
+
+    def close(self):
+        try:
+            self.b.close()
+        except (BufferError, ValueError):      # views into the map are still alive: the map goes with them
+            pass
+        self._fh.close()
+
+    def _layout(self, name):
+        for mtype, data in self._messages(self.datasets[name]):
+            if mtype == 0x0008:
+                return data
+        raise KeyError(name)
+
+    def is_chunked(self, name):
+        return self._layout(name)[1] == 2
+
+    def frame_view(self, name, t):
+        """Frame t of a chunked dataset as a read-only array over the file mapping (no copy); a frame that was
+        never written reads as zeros (the HDF5 fill value)."""
+        shape = self.shape(name)
+        layout = self._layout(name)
+        assert layout[0] == 3 and layout[1] == 2
+        if name not in self._chunks:
+            self._chunks[name] = {}
+            self._walk(struct.unpack_from("<Q", layout, 3)[0], layout[2], self._chunks[name])
+        fshape = tuple(shape[:-1])
+        addr = self._chunks[name].get(int(t))
+        if addr is None:
+            return np.zeros(fshape)
+        return np.frombuffer(self.b, "<f8", int(np.prod(fshape)), addr).reshape(fshape)
 
     def read(self, name, frame=None):
         """Whole dataset (contiguous, or chunked with all frames present) or one time frame."""

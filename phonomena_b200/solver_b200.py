@@ -145,7 +145,11 @@ class Writer:
             self.written, self.wait_seconds, self.write_seconds = getattr(self.e, "writer_stats", (0, 0.0, 0.0))
             self.h5.keep_frames(self.written)
         self.h5.attrs["frames_written"] = int(self.written)
-        self.h5.close()
+        try:
+            self.h5.close()
+        except OSError as exc:          # the error that stopped the writer threads (ENOSPC, ...) usually hits the metadata too
+            if self.error is None:
+                self.error = exc
         if self.error is not None:
             raise self.error
 
