@@ -325,11 +325,13 @@ def run_b200(args):
     e2e = None
     if not args.no_e2e:
         fields = tuple(args.e2e_fields.split(","))
-        e2e = run_e2e(case, n, rank, local, K, dtype, arith, dist, fields=fields, steps=max(K, args.e2e_steps))
+        e2e_steps = max(K, args.e2e_steps)
+        every = args.e2e_record_every or (1 if e2e_steps <= 2000 else -(-e2e_steps // 1000))     # long runs: <= 1000 frames
+        e2e = run_e2e(case, n, rank, local, K, dtype, arith, dist, fields=fields, steps=e2e_steps, record_every=every)
         if n == 1 and e2e["file_dir"] != args.disk_dir and not args.no_disk:
             # the same run with the output on the temp directory's file system (the default above is tmpfs)
             try:
-                d2 = run_e2e(case, n, rank, local, K, dtype, arith, dist, fields=fields, steps=max(K, args.e2e_steps), out_dir=args.disk_dir)
+                d2 = run_e2e(case, n, rank, local, K, dtype, arith, dist, fields=fields, steps=e2e_steps, out_dir=args.disk_dir, record_every=every)
                 e2e["disk"] = {k: d2[k] for k in ("value", "file_dir", "run_ms", "init_s", "writer_write_ms", "writer_wait_ms", "steps")}
             except Exception as exc:
                 e2e["disk"] = {"error": str(exc)[:200]}
@@ -399,7 +401,7 @@ def cpu_baseline_leg():
     return {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample + " (oracle/_ref absent)"}
 
 
-def run_e2e(case, n, rank, local, K, dtype, arith, dist, fields=("ux", "uy", "uz"), steps=200, out_dir=None):
+def run_e2e(case, n, rank, local, K, dtype, arith, dist, fields=("ux", "uy", "uz"), steps=200, out_dir=None, record_every=1):
     """Solver.init + Solver.run through the plugin with host buffers: mesh lines, inclusion list
     and tables go host->device in init(); inside the timed run() every chunk's source samples go
     host->device and every step's surface planes come back through the pinned ring into the HDF5
@@ -410,7 +412,7 @@ def run_e2e(case, n, rank, local, K, dtype, arith, dist, fields=("ux", "uy", "uz
     g, m = case.as_grid_material()
     s = Solver()
     s.cfg.update({"precision": {"f64": "fp64", "f32": "fp32"}[dtype], "arith": arith, "device": local, "wave": "sin",
-                  "wave_args": {"f": 100}, "write_mode": "thread", "record": "surface", "record_every": 1,
+                  "wave_args": {"f": 100}, "write_mode": "thread", "record": "surface", "record_every": int(record_every),
                   "slabs_from_env": n > 1, "chunk_steps": 25,
                   "record_fields": list(fields),
                   "merge_slabs": False})      # N > 1: one slab file per rank (concatenating them is post-processing)
@@ -419,7 +421,7 @@ def run_e2e(case, n, rank, local, K, dtype, arith, dist, fields=("ux", "uy", "uz
     # the temp directory (e2e["disk"])
     nx, ny, nz = case.shape
     frame_bytes = 8 * sum(v for k, v in (("ux", (nx - 1) * ny), ("uy", nx * (ny - 1)), ("uz", nx * ny)) if k in fields) // n
-    need = frame_bytes * steps + 9 * nx * ny * nz // n + (1 << 28)
+    need = frame_bytes * (steps // record_every) + 9 * nx * ny * nz // n + (1 << 28)
     if out_dir is None:
         out_dir = tempfile.gettempdir()
         try:
@@ -456,8 +458,9 @@ def run_e2e(case, n, rank, local, K, dtype, arith, dist, fields=("ux", "uy", "uz
     path = s.file if n == 1 else "%s.rank%d" % (s.file, rank)
     out = {"value": nx * ny * nz * steps / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": 8,
            "d2h_bytes_per_step": 8 * sum(v for k, v in (("ux", (nx - 1) * ny), ("uy", nx * (ny - 1)), ("uz", nx * ny)) if k in fields),
-           "steps": steps,
-           "what": "Solver.run(): source sample H2D + surface %s planes D2H (pinned ring) -> native writer threads -> HDF5 every step" % ",".join(fields)
+           "steps": steps, "record_every": int(record_every),
+           "what": "Solver.run(): source sample H2D + surface %s planes D2H (pinned ring) -> native writer threads -> HDF5 every %s" % (
+                   ",".join(fields), "step" if record_every == 1 else "%d steps (long run: the byte counts are per recorded step)" % record_every)
                    + ("; one slab file per rank, max over ranks" if n > 1 else ""),
            "file_bytes": os.path.getsize(path), "file_dir": out_dir, "init_s": init_s,
            "frames_written": int(s.writer.written) if s.writer is not None else 0,
@@ -505,6 +508,7 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: 512 planes per GPU (config #3 / #5); strong: the fixed 1024x512x512 grid of config #4 split over the GPUs")
     ap.add_argument("--e2e-steps", type=int, default=200, help="the e2e run() is timed over max(K, this) steps")
+    ap.add_argument("--e2e-record-every", type=int, default=0, help="0 = every step up to 2000 e2e steps, else so that <= 1000 frames are written")
     ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the slab-vs-single-GPU check before the timed region")
     ap.add_argument("--no-disk", action="store_true", help="N = 1: skip the second e2e run with the output on --disk-dir")
     ap.add_argument("--disk-dir", default=__import__("tempfile").gettempdir())

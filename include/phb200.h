@@ -41,9 +41,12 @@ enum { PHB_F32 = 0, PHB_F64 = 1 };
  *             fp64 results are BIT-IDENTICAL to the reference's NumPy evaluation. */
 enum { PHB_FAST = 0, PHB_EXACT = 1, PHB_COMP = 2 };
 /*  PHB_COMP : FAST arithmetic on the compensated state (u, delta = u - u_old) instead of (u, u_old):
- *             delta += dt^2/rho * div T;  u_new = u + delta.  Same step algebraically; keeps fp32 within
- *             1e-5 of the reference over >= 10^4 steps (plain fp32 drifts to 6e-5), at 12 instead of 9
- *             field words of traffic per cell. */
+ *             delta += dt^2/rho * div T;  u_new = u + delta.  Same step algebraically, several times less
+ *             fp32 round-off drift on long runs, at 12 instead of 9 field words of traffic per cell.
+ *             Measured on data/default.json (tests/test_gpu_long.py): rel-L2 vs the reference after 10^3 /
+ *             10^4 steps: plain fp32 2.9e-6 / 5.9e-5, PHB_COMP 3.4e-7 / 1.45e-5 -- i.e. fp32 meets the 1e-5
+ *             north-star tolerance up to a few thousand steps (plain) or ~7000 steps (PHB_COMP), NOT over
+ *             10^4; use fp64 (1e-13 after 10^4 steps) when 1e-5 must hold on longer runs. */
 /* stencil kernel selection: MARCH = the TMA-fed x-marching kernel (k_march.cuh), NAIVE = one thread per cell
  * (k_naive.cuh, the on-device specification); AUTO = MARCH except on slabs below 200 000 cells (too few tiles
  * for the serial x-march) and when the stencil-class table does not fit beside the shared-memory rings */
@@ -53,6 +56,12 @@ enum { PHB_CUR = 0, PHB_OLD = 1 };
 /* surface components to record (bit mask) */
 enum { PHB_REC_UX = 1, PHB_REC_UY = 2, PHB_REC_UZ = 4,
        PHB_REC_FULL = 8 };   /* frames hold the whole arrays (reference shapes, z fastest) instead of their k = 0 planes */
+
+/* y boundaries.  ABSORBING: first-order Mur faces at y = 0 and y = -1 (base_solver.py:543-550), what the reference
+ * runs.  PERIODIC: the reference's archived stubs apply_T_pbc / apply_u_pbc (base_solver.py:383-400,
+ * 475-486; zero Bloch phase), each applied after the corresponding traction-free update, and no Mur face in y; the x and
+ * z faces stay.  Not available with PHB_COMP; slab contexts exchange halos through NCCL in this mode. */
+enum { PHB_BC_ABSORBING = 0, PHB_BC_PERIODIC = 1 };
 
 typedef struct phb_cfg {
     int32_t nx, ny, nz;      /* global grid points: grid.x.size, grid.y.size, grid.z.size        */
@@ -64,7 +73,8 @@ typedef struct phb_cfg {
     int32_t record_mask;     /* PHB_REC_* bits; 0 = no surface recording                          */
     int32_t record_every;    /* record the k=0 plane after every n-th step (>=1)                  */
     int32_t ring_slots;      /* pinned-host ring depth (frames); 0 = default                      */
-    int32_t reserved[4];
+    int32_t bc_y;            /* PHB_BC_ABSORBING (0, the reference's behaviour) | PHB_BC_PERIODIC                */
+    int32_t reserved[3];
     double  dt;              /* material.dt                                      (material.py:80-93) */
     double  d2;              /* dt**2 as evaluated by the host (base_solver.py:443: self.m.dt**2) */
 } phb_cfg;

@@ -163,7 +163,9 @@ class OracleSolver:
     write disjoint arrays).
     """
 
-    def __init__(self, x, y, z, C, P, dt, wave="sin", wave_args=None, threads=1):
+    def __init__(self, x, y, z, C, P, dt, wave="sin", wave_args=None, threads=1, bc_y="absorbing"):
+        assert bc_y in ("absorbing", "periodic")
+        self.bc_y = bc_y
         self.x = np.asarray(x, F64)
         self.y = np.asarray(y, F64)
         self.z = np.asarray(z, F64)
@@ -369,6 +371,35 @@ class OracleSolver:
         ny_[:, :, -1] = uy[:, :, -2] + c["ctz"] * (ny_[:, :, -2] - uy[:, :, -1])
         nz_[:, :, -1] = uz[:, :, -2] + c["clz"] * (nz_[:, :, -2] - uz[:, :, -1])
 
+    # -- periodic y boundaries: the reference's ARCHIVED stubs (base_solver.py:383-400, 475-486), zero Bloch phase --
+    def apply_T_pbc(self):
+        """base_solver.py:388-400, the uncommented lines."""
+        self.T1[:, 0, :] = self.T1[:, -2, :]
+        self.T2[:, 0, :] = self.T2[:, -2, :]
+        self.T3[:, 0, :] = self.T3[:, -2, :]
+        self.T5[:, 0, :] = self.T5[:, -2, :]
+        self.T4[:, -1, :] = self.T4[:, 1, :]
+        self.T6[:, -1, :] = self.T6[:, 1, :]
+
+    def apply_u_pbc(self):
+        """base_solver.py:480-486, the uncommented lines."""
+        self.ux_new[:, 0, :] = self.ux_new[:, -2, :]
+        self.uz_new[:, 0, :] = self.uz_new[:, -2, :]
+        self.uy_new[:, -1, :] = self.uy_new[:, 1, :]
+
+    def apply_u_abc_xz(self):
+        """The x = -1 and z = -1 faces of apply_u_abc (base_solver.py:539-542, 551-554); the y faces are what the
+        periodic copies replace."""
+        c = self.abc_coefficients()
+        ux, uy, uz = self.ux, self.uy, self.uz
+        nx_, ny_, nz_ = self.ux_new, self.uy_new, self.uz_new
+        nx_[-1, :, :] = ux[-2, :, :] + c["clx"] * (nx_[-2, :, :] - ux[-1, :, :])
+        ny_[-1, :, :] = uy[-2, :, :] + c["ctx"] * (ny_[-2, :, :] - uy[-1, :, :])
+        nz_[-1, :, :] = uz[-2, :, :] + c["ctx"] * (nz_[-2, :, :] - uz[-1, :, :])
+        nx_[:, :, -1] = ux[:, :, -2] + c["ctz"] * (nx_[:, :, -2] - ux[:, :, -1])
+        ny_[:, :, -1] = uy[:, :, -2] + c["ctz"] * (ny_[:, :, -2] - uy[:, :, -1])
+        nz_[:, :, -1] = uz[:, :, -2] + c["clz"] * (nz_[:, :, -2] - uz[:, :, -1])
+
     # -- A.6  time_step  (base_solver.py:556-571) -----------------------------
     def time_step(self):
         """Copy-based shift exactly as the reference: afterwards ``u_new == u``
@@ -385,9 +416,15 @@ class OracleSolver:
         self.uz[0, :, 0] = w
         self.update_T()
         self.apply_T_tfbc()
+        if self.bc_y == "periodic":          # each stub right after the corresponding traction-free update
+            self.apply_T_pbc()
         self.update_u()
         self.apply_u_tfbc()
-        self.apply_u_abc()
+        if self.bc_y == "periodic":
+            self.apply_u_pbc()
+            self.apply_u_abc_xz()
+        else:
+            self.apply_u_abc()
         self.time_step()
         self.tt += 1
 

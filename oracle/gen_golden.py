@@ -22,8 +22,45 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
 
 
-def _run(grid, material, cfg, steps, snaps=()):
-    s = refshim.default_solver()
+def periodic_y_solver():
+    """The reference solver with its ARCHIVED periodic stubs switched on: a subclass of the unmodified
+    solver_default.Solver whose update_T_BC / update_u_BC (the two hooks the reference provides for exactly this,
+    base_solver.py:374-381, 465-473) call the reference's own apply_T_pbc / apply_u_pbc (:383-400, :475-486), each right
+    after the corresponding traction-free update, and then the x and z faces of the Mur ABC (the y faces are what the
+    periodic copies replace; their lines of apply_u_abc, :543-550, are left out -- the other six are restated below
+    because the reference has them in one function)."""
+    refshim.install()
+    from simulation.solvers import solver_default
+
+    class PeriodicY(solver_default.Solver):
+        def update_T_BC(self):
+            self.apply_T_tfbc()
+            self.apply_T_pbc()
+
+        def update_u_BC(self):
+            self.apply_u_tfbc()
+            self.apply_u_pbc()
+            g, m = self.g, self.m
+            vl = np.sqrt(m.C[0, 0, 0, 0, 0] / m.P[0, 0, 0])
+            vt = np.sqrt(m.C[0, 0, 0, 3, 3] / m.P[0, 0, 0])
+            ctx = ((vt * m.dt - g.fdx) / (vt * m.dt + g.fdx))[:, 0, 0]
+            clx = ((vl * m.dt - g.sdx) / (vl * m.dt + g.sdx))[:, 0, 0]
+            ctz = ((vt * m.dt - g.fdz) / (vt * m.dt + g.fdz))[0, 0, :]
+            clz = ((vl * m.dt - g.sdz) / (vl * m.dt + g.sdz))[0, 0, :]
+            g.ux_new[-1, :, :] = g.ux[-2, :, :] + clx[-1] * (g.ux_new[-2, :, :] - g.ux[-1, :, :])
+            g.uy_new[-1, :, :] = g.uy[-2, :, :] + ctx[-1] * (g.uy_new[-2, :, :] - g.uy[-1, :, :])
+            g.uz_new[-1, :, :] = g.uz[-2, :, :] + ctx[-1] * (g.uz_new[-2, :, :] - g.uz[-1, :, :])
+            g.ux_new[:, :, -1] = g.ux[:, :, -2] + ctz[-1] * (g.ux_new[:, :, -2] - g.ux[:, :, -1])
+            g.uy_new[:, :, -1] = g.uy[:, :, -2] + ctz[-1] * (g.uy_new[:, :, -2] - g.uy[:, :, -1])
+            g.uz_new[:, :, -1] = g.uz[:, :, -2] + clz[-1] * (g.uz_new[:, :, -2] - g.uz[:, :, -1])
+
+    s = PeriodicY()
+    s.cfg["write_mode"] = "off"
+    return s
+
+
+def _run(grid, material, cfg, steps, snaps=(), solver=None):
+    s = solver if solver is not None else refshim.default_solver()
     s.cfg.update(cfg)
     s.cfg["write_mode"] = "off"
     s.init(grid, material, steps)
@@ -94,7 +131,7 @@ def case_settings(name, path, steps, snaps, cfg_over=None):
 
 
 def case_custom(name, size, max_d, min_d, incl, steps, snaps, wave, wave_args, courant=0.1,
-                primary="GaAs", secondary="Au"):
+                primary="GaAs", secondary="Au", periodic_y=False):
     common = refshim.install()
     from simulation import grid as rgrid, material as rmat
     props = json.load(open(os.path.join(refshim.REF_ROOT, "data", "default.json")))["material"]["properties"]
@@ -113,8 +150,8 @@ def case_custom(name, size, max_d, min_d, incl, steps, snaps, wave, wave_args, c
     m.setPrimary(primary)
     m.setSecondary(secondary)
     m.update()
-    s, fr = _run(g, m, {"wave": wave, "wave_args": wave_args}, steps, snaps)
-    _pack(name, s, fr, steps, courant)
+    s, fr = _run(g, m, {"wave": wave, "wave_args": wave_args}, steps, snaps, solver=periodic_y_solver() if periodic_y else None)
+    _pack(name, s, fr, steps, courant, extra={"bc_y": "periodic"} if periodic_y else None)
 
 
 def case_spectrum(name, path, steps, y_index, x_index):
@@ -167,6 +204,12 @@ def main():
     case_custom("crystal_48x32x12", (47, 31, 11), (1, 1, 1), 1,
                 [(8.0 + 16 * a, 8.0 + 16 * b, 11.0, 4.0) for a in range(3) for b in range(2)][:5],
                 80, (1, 80), "sin", {"f": 100})
+    # periodic y boundaries: the reference's archived stubs switched on (periodic_y_solver above);
+    # a crystal strip one lattice period wide in y with a non-uniform x mesh, and a homogeneous block
+    case_custom("periodic_y_crystal_40x18x14", (39, 17, 13), (1.4, 1, 1), 0.5,
+                [(10.0, 8.0, 13.0, 3.5), (26.0, 8.0, 6.0, 3.0)], 120, (1, 2, 40, 120), "sin", {"f": 100}, periodic_y=True)
+    case_custom("periodic_y_homog_24x12x10", (23, 11, 9), (1, 1, 1), 1, [], 60, (1, 60), "ricker", {"f": 100},
+                secondary="GaAs", periodic_y=True)
     case_spectrum("spectrum_default_json_128", os.path.join(ref, "data", "default.json"), 128, 10, 5)
 
 

@@ -19,6 +19,7 @@ FAST, EXACT, COMP = 0, 1, 2
 KERNEL_AUTO, KERNEL_NAIVE, KERNEL_MARCH = 0, 1, 2
 CUR, OLD = 0, 1
 REC_UX, REC_UY, REC_UZ, REC_FULL = 1, 2, 4, 8
+BC_ABSORBING, BC_PERIODIC = 0, 1
 
 # every symbol include/phb200.h declares (tests check the .so exports all of them)
 SYMBOLS = (
@@ -46,7 +47,7 @@ class Cfg(C.Structure):
         ("x0", C.c_int32), ("nxl", C.c_int32),
         ("dtype", C.c_int32), ("arith", C.c_int32), ("device", C.c_int32), ("kernel", C.c_int32),
         ("record_mask", C.c_int32), ("record_every", C.c_int32), ("ring_slots", C.c_int32),
-        ("reserved", C.c_int32 * 4),
+        ("bc_y", C.c_int32), ("reserved", C.c_int32 * 3),
         ("dt", C.c_double), ("d2", C.c_double),
     ]
 
@@ -164,7 +165,7 @@ class Engine:
     """One device context = one grid or one x-slab [x0, x0+nxl) on one GPU."""
 
     def __init__(self, nx, ny, nz, dt, d2=None, dtype="f64", arith="fast", device=0, x0=0, nxl=None,
-                 kernel="auto", record_mask=0, record_every=1, ring_slots=0):
+                 kernel="auto", record_mask=0, record_every=1, ring_slots=0, bc_y="absorbing"):
         self.lib = load_library()
         self.nx, self.ny, self.nz = int(nx), int(ny), int(nz)
         self.x0 = int(x0)
@@ -176,6 +177,8 @@ class Engine:
         cfg.dtype, cfg.arith, cfg.device = self.dtype, self.arith, int(device)
         cfg.kernel = {"auto": KERNEL_AUTO, "naive": KERNEL_NAIVE, "march": KERNEL_MARCH}[kernel]
         cfg.record_mask, cfg.record_every, cfg.ring_slots = int(record_mask), int(record_every), int(ring_slots)
+        cfg.bc_y = {"absorbing": BC_ABSORBING, "periodic": BC_PERIODIC}[bc_y]
+        self.bc_y = bc_y
         cfg.dt = float(dt)
         # the reference evaluates self.m.dt**2 in Python (base_solver.py:443)
         cfg.d2 = float(dt ** 2 if d2 is None else d2)

@@ -154,7 +154,11 @@ struct Eval {
     const Geo<T> &g;
     const Fld<T> &u;
     const M &m;
-    __device__ Eval(const Geo<T> &g_, const Fld<T> &u_, const M &m_) : g(g_), u(u_), m(m_) {}
+    // Periodic y boundaries, zero Bloch phase -- the reference's archived apply_T_pbc (base_solver.py:383-400), applied
+    // after the traction-free stresses: T1, T2, T3, T5 on row 0 are those of row ny-2; T4, T6 on their last row (ny-2)
+    // are those of row 1.
+    bool pbc;
+    __device__ Eval(const Geo<T> &g_, const Fld<T> &u_, const M &m_, bool pbc_ = false) : g(g_), u(u_), m(m_), pbc(pbc_) {}
 
     // coefficient e of the class of cell (i,j,k)
     __device__ __forceinline__ T coef(int i, int j, int k, int e) const {
@@ -164,6 +168,7 @@ struct Eval {
     // T1, T2, T3 at node (i,j,k)
     __device__ __forceinline__ void normal(int i, int j, int k, T &t1, T &t2, T &t3) const {
         t1 = t2 = t3 = (T)0;
+        if (pbc && j == 0) j = g.ny - 2;
         if (i < 1 || i > g.nx - 2 || j < 1 || j > g.ny - 2 || k < 0 || k > g.nz - 2) return;
         const bool k0 = (k == 0);
         const T dxx = A::sub(u.ux[g.idx(i, j, k)], u.ux[g.idx(i - 1, j, k)]);
@@ -180,6 +185,7 @@ struct Eval {
         t3 = k0 ? (T)0 : normal_row<A>(c + 6, dxx, dyy, dzz, sx, sy, sz);
     }
     __device__ __forceinline__ T t4(int i, int j, int k) const {
+        if (pbc && j == g.ny - 2) j = 1;
         if (i < 1 || i > g.nx - 2 || j < 0 || j > g.ny - 2 || k < 0 || k > g.nz - 2) return (T)0;
         const bool k0 = (k == 0);
         const T a = A::sub(u.uy[g.idx(i, j, k + 1)], u.uy[g.idx(i, j, k)]);
@@ -187,6 +193,7 @@ struct Eval {
         return shear<A>(coef(i, j, k, CLS_C44), a, k0 ? g.fdy0 : g.fdz[k], b, k0 ? g.fdz0 : g.fdy[j]);
     }
     __device__ __forceinline__ T t5(int i, int j, int k) const {
+        if (pbc && j == 0) j = g.ny - 2;
         if (i < 0 || i > g.nx - 2 || j < 1 || j > g.ny - 2 || k < 0 || k > g.nz - 2) return (T)0;
         const bool k0 = (k == 0);
         const T a = A::sub(u.ux[g.idx(i, j, k + 1)], u.ux[g.idx(i, j, k)]);
@@ -194,6 +201,7 @@ struct Eval {
         return shear<A>(coef(i, j, k, CLS_C55), a, k0 ? g.fdx0 : g.fdz[k], b, k0 ? g.fdz0 : g.fdx[i]);
     }
     __device__ __forceinline__ T t6(int i, int j, int k) const {
+        if (pbc && j == g.ny - 2) j = 1;
         if (i < 0 || i > g.nx - 2 || j < 0 || j > g.ny - 2 || k < 0 || k > g.nz - 2) return (T)0;
         const bool k0 = (k == 0);
         const T a = A::sub(u.ux[g.idx(i, j + 1, k)], u.ux[g.idx(i, j, k)]);

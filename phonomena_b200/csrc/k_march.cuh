@@ -256,7 +256,7 @@ k_step_march(const __grid_constant__ MarchMaps tm, StepArgs<typename A::T> p, Ma
 
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int r0 = w * RW;                           // first tile row of this warp (rows r0 .. r0 + RW - 1)
-    const int k0t = blockIdx.x * TZ;                 // first cell of the tile row
+    const int k0t = (blockIdx.x + p.ztile0) * TZ;    // first cell of the tile row
     const int j0 = blockIdx.y * C_::TY;              // first output row
     // planes [ia, ib): x-chunk blockIdx.z of [i_begin, i_end), or (edge launch) the single planes i_begin / edge_b
     const int ia = (p.edge_b >= 0) ? (blockIdx.z == 0 ? p.i_begin : p.edge_b) : p.i_begin + blockIdx.z * chunk;
@@ -366,7 +366,7 @@ k_step_march(const __grid_constant__ MarchMaps tm, StepArgs<typename A::T> p, Ma
     const int xS = (w >= 1) ? -TZ : 0, xN = (w <= W - 2) ? TZ : 0;
     const uint32_t pubO = bar_pub + (uint32_t)w * 16;
     // lane that holds k = nz-2, nz-1 if this block applies the z face itself, else -1
-    const int zlane = (ZF && k0t <= g.nz - 1 && g.nz - 1 < k0t + TZ) ? (g.nz - 1 - k0t) / V : -1;
+    const int zlane = (ZF && p.zface == 1 && k0t <= g.nz - 1 && g.nz - 1 < k0t + TZ) ? (g.nz - 1 - k0t) / V : -1;   // zface == 2: timing aid (face code resident, never run)
     const T *const zt = ztab + lane * V;               // this lane's z spacings
     const T *const yt = ytab + 2 * r0;
 
@@ -822,11 +822,11 @@ template <class T> inline const char *march_name() { return "march_tma"; }
 // returns launches made (1), 0 for an empty range, -1 if the shared-memory request is refused
 template <class A, int R, int NST, int RW = 1, bool PUSH = false>
 inline int launch_march_cfg(const StepArgs<typename A::T> &p, const MatCls<typename A::T> &m, const MarchMaps &maps,
-                            int chunks, cudaStream_t st) {
+                            int chunks, cudaStream_t st, int ntiles = 0) {
     using T = typename A::T;
     using C_ = MarchCfg<T, R, NST, RW>;
     if constexpr (!PUSH) {
-        if (p.push_lo[0] || p.push_hi[0]) return launch_march_cfg<A, R, NST, RW, true>(p, m, maps, chunks, st);
+        if (p.push_lo[0] || p.push_hi[0]) return launch_march_cfg<A, R, NST, RW, true>(p, m, maps, chunks, st, ntiles);
     }
     constexpr bool kHasZF = (RW == 2) && !A::COMP;     // instantiations with the fused z face (StepArgs::zface)
     if (p.zface && !kHasZF) return -3;
@@ -849,7 +849,8 @@ inline int launch_march_cfg(const StepArgs<typename A::T> &p, const MatCls<typen
         }
         attr_bytes = smem;
     }
-    dim3 grid((p.g.nzp + C_::TZ - 1) / C_::TZ, (p.g.ny + C_::TY - 1) / C_::TY, p.edge_b >= 0 ? 2 : (np + chunk - 1) / chunk);
+    // ntiles > 0: z-tiles [p.ztile0, p.ztile0 + ntiles) only
+    dim3 grid(ntiles > 0 ? ntiles : (p.g.nzp + C_::TZ - 1) / C_::TZ, (p.g.ny + C_::TY - 1) / C_::TY, p.edge_b >= 0 ? 2 : (np + chunk - 1) / chunk);
     kern<<<grid, C_::W * 32, smem, st>>>(maps, p, m, chunk);
     return 1;
 }

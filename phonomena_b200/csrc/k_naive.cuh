@@ -22,16 +22,18 @@ struct StepArgs {
     // lane); the host then re-applies the face only where the x / y faces change its inputs (k_abc_z, edges only)
     int zface;
     T zf_ct, zf_cl;
+    int ztile0;           // k_march only: first z-tile of this launch (the step may be split into a launch for the z-tiles
+                          // without the face and one for the tile that owns it, see phb200.cu physics())
 };
 
 // u_new for one cell from generic stress evaluations.  Writes only entries the reference's
 // physics writes (App. A.3/A.4 ranges) plus the i = 0 copy that keeps `u_new == u` where
 // nothing is ever written (App. B #9).
 template <class A, class M>
-__device__ __forceinline__ void naive_cell(const StepArgs<typename A::T> &p, const M &m, int i, int j, int k) {
+__device__ __forceinline__ void naive_cell(const StepArgs<typename A::T> &p, const M &m, int i, int j, int k, bool pbc = false) {
     using T = typename A::T;
     const Geo<T> &g = p.g;
-    Eval<A, M> ev(g, p.cur, m);
+    Eval<A, M> ev(g, p.cur, m, pbc);
     const bool k0 = (k == 0);
     const long long c = g.idx(i, j, k);
     if (k > g.nz - 2) return;   // k = nz-1: ABC face (ux, uy) / non-existent (uz)
@@ -120,17 +122,46 @@ __global__ void __launch_bounds__(256) k_step_naive(StepArgs<typename A::T> p, M
     naive_cell<A, M>(p, m, i, j, k);
 }
 
+// Periodic y boundaries (zero Bloch phase): the reference's archived stubs apply_T_pbc / apply_u_pbc
+// (base_solver.py:383-400, 475-486), each applied after the corresponding traction-free update, in place of the
+// y faces of the Mur ABC.  The stress copies only reach three rows of u_new -- ux and uz on row ny-2 (through T6 / T4
+// of that row = those of row 1) and uy on row 0 (through T2 of row 0 = that of row ny-2) -- so the step kernels run
+// unchanged and this kernel recomputes those rows from the current field with the wrapped stresses (same formula
+// functions, so EXACT arithmetic stays bit-identical), then makes the displacement copies
+//   ux_new[:,0,:] = ux_new[:,-2,:];  uz_new[:,0,:] = uz_new[:,-2,:];  uy_new[:,-1,:] = uy_new[:,1,:]
+// and keeps u_new == u on the rows nothing writes in this mode (ux, uz on row ny-1).
+// threads over (k, i); planes [i_begin, i_end).
+template <class A, class M>
+__global__ void __launch_bounds__(256) k_pbc_y(StepArgs<typename A::T> p, M m) {
+    const Geo<typename A::T> &g = p.g;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = p.i_begin + blockIdx.y * blockDim.y + threadIdx.y;
+    if (k >= g.nz || i >= p.i_end) return;
+    naive_cell<A, M>(p, m, i, g.ny - 2, k, true);
+    naive_cell<A, M>(p, m, i, 0, k, true);
+    const long long r0 = g.idx(i, 0, k), r1 = g.idx(i, 1, k), rm = g.idx(i, g.ny - 2, k), rl = g.idx(i, g.ny - 1, k);
+    if (i <= g.nx - 2) {
+        p.nw.ux[r0] = p.nw.ux[rm];
+        p.nw.ux[rl] = p.cur.ux[rl];
+    }
+    if (k <= g.nz - 2) {
+        p.nw.uz[r0] = p.nw.uz[rm];
+        p.nw.uz[rl] = p.cur.uz[rl];
+    }
+    p.nw.uy[rm] = p.nw.uy[r1];
+}
+
 // Stress dump in the reference's array shapes (double), for phb_get_stress.
 // nT1 planes etc. are the owned plane counts; out arrays are plane-major like the host arrays.
 template <class A, class M>
 __global__ void k_stress_dump(Geo<typename A::T> g, Fld<typename A::T> u, M m, int i_begin, int i_end,
-                              double *T1, double *T2, double *T3, double *T4, double *T5, double *T6) {
+                              double *T1, double *T2, double *T3, double *T4, double *T5, double *T6, bool pbc) {
     using T = typename A::T;
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y * blockDim.y + threadIdx.y;
     const int i = i_begin + blockIdx.z;
     if (k >= g.nz || j >= g.ny || i >= i_end) return;
-    Eval<A, M> ev(g, u, m);
+    Eval<A, M> ev(g, u, m, pbc);
     const long long li = i - i_begin;
     T t1, t2, t3;
     ev.normal(i, j, k, t1, t2, t3);

@@ -121,6 +121,9 @@ struct phb_ctx {
     size_t esz = 0;            // sizeof(T)
     int device = 0;
     cudaStream_t st = nullptr, cst = nullptr;
+    cudaStream_t zst = nullptr;        // second launch stream of a split step (the z-tile that owns the z = -1 face)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int zsplit = 1;                    // PHB_ZSPLIT=0: one launch for all z-tiles
     cudaEvent_t ev_edge = nullptr, ev_comm = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
     void *buf[3][3] = {};      // [buffer][component], each (nxl+2) planes
     int cur = 0;               // buffer holding u; old = (cur+2)%3, new = (cur+1)%3
@@ -424,7 +427,7 @@ struct Engine : IEngine {
         (void)nx;
         MatCls<T> m = mat();
         auto run = [&]<class A>() -> int {
-            k_stress_dump<A, MatCls<T>><<<gr, bl, 0, c->st>>>(g, u, m, ib, ie, d[0], d[1], d[2], d[3], d[4], d[5]);
+            k_stress_dump<A, MatCls<T>><<<gr, bl, 0, c->st>>>(g, u, m, ib, ie, d[0], d[1], d[2], d[3], d[4], d[5], periodic_y());
             return 0;
         };
         int r = dispatch(run);
@@ -461,8 +464,11 @@ struct Engine : IEngine {
         p.cur = fld(b_cur()); p.old = fld(b_old()); p.nw = fld(b_new());
         p.line_save = (c->w && c->cfg.x0 == 0) ? (const T *)c->line_save : nullptr;
         p.i_begin = ib; p.i_end = ie;
+        p.ztile0 = 0;
         const bool march = use_march();
         p.zface = (march && zface_fused()) ? 1 : 0;
+        static const int zf_nop = getenv("PHB_DEBUG_ZF_NOP") ? atoi(getenv("PHB_DEBUG_ZF_NOP")) : 0;   // timing aid: ZF instantiation, face never applied
+        if (zf_nop && march && !comp() && c->mRW == 2) p.zface = 2;
         p.zf_cl = (T)c->abc[6]; p.zf_ct = (T)c->abc[7];
         std::pair<cudaEvent_t, cudaEvent_t> *pe = nullptr;
         if (c->prof) {
@@ -486,6 +492,26 @@ struct Engine : IEngine {
                 const MarchMaps &mp = c->mm[b_cur()];
                 const int ch = plan_chunks(ie - ib);
                 int r = -2;
+                // Split step: the z = -1 face code costs the stencil kernel more through its instruction footprint (the
+                // plane loop no longer fits the 32 KB instruction cache level, every block pays) than through the work
+                // itself (only the blocks of the last z-tile run it).  So the tile that owns the face is launched on its
+                // own with the face instantiation, on a second (higher-priority) stream beside the launch for all other
+                // z-tiles without it; both finish inside the same waves of blocks.
+                const int V = VecOf<T>::V, nzt = (c->nzp + 32 * V - 1) / (32 * V);
+                if (p.zface == 1 && c->zsplit && nzt >= 2 && edge_b < 0 && c->mR == 16 && c->mNST == 4 && c->mRW == 2) {
+                    CU(cudaEventRecord(c->ev_fork, c->st));
+                    CU(cudaStreamWaitEvent(c->zst, c->ev_fork, 0));
+                    StepArgs<T> pz = p;
+                    pz.ztile0 = nzt - 1;
+                    const int rz = launch_march_cfg<A, 16, 4, 2>(pz, m, mp, ch, c->zst, 1);
+                    CU(cudaEventRecord(c->ev_join, c->zst));
+                    p.zface = 0;
+                    r = launch_march_cfg<A, 16, 4, 2>(p, m, mp, ch, c->st, nzt - 1);
+                    CU(cudaStreamWaitEvent(c->st, c->ev_join, 0));
+                    if (rz < 0 || r < 0) return fail("marching kernel needs more shared memory than the device allows (%d classes)", c->ncls);
+                    c->launches += rz + r;
+                    return 0;
+                }
                 if (c->mR == 16 && c->mNST == 4 && c->mRW == 2) r = launch_march_cfg<A, 16, 4, 2>(p, m, mp, ch, c->st);
                 else if (c->mR == 16 && c->mNST == 4) r = launch_march_cfg<A, 16, 4>(p, m, mp, ch, c->st);
                 else if (c->mR == 16 && c->mNST == 3) r = launch_march_cfg<A, 16, 3>(p, m, mp, ch, c->st);
@@ -515,7 +541,8 @@ struct Engine : IEngine {
         const int V = VecOf<T>::V, nz = c->cfg.nz;
         // measured at 512^3: fp32 gains 4 % (the separate strided face kernel costs 48 us per step), fp64 loses about as much
         // in the stencil kernel itself as the face kernel costs -> default on for fp32 only (PHB_ZFUSE=0/1 overrides)
-        const bool want = c->zfuse < 0 ? (sizeof(T) == 4) : (c->zfuse != 0);
+        // round 2: with the split step (physics()) the fused face pays in fp64 too -> on by default for both types
+        const bool want = c->zfuse < 0 ? true : (c->zfuse != 0);
         if (!want || comp() || c->mRW != 2 || nz < 2 * V || nz % V != 0) return false;
         return ((nz - 1) % (32 * V)) / V >= 1;
     }
@@ -592,11 +619,32 @@ struct Engine : IEngine {
         CU(cudaGetLastError());
         return 0;
     }
+    bool periodic_y() const { return c->cfg.bc_y == PHB_BC_PERIODIC; }
+    // periodic y boundaries: recompute the rows the wrapped stresses reach + the displacement copies (k_pbc_y); must run
+    // right after the stencil launch of the same planes, BEFORE the x face (the reference order: pbc, then apply_u_abc)
+    int pbc_y(int ib, int ie) {
+        if (ie <= ib || !periodic_y()) return 0;
+        StepArgs<T> p;
+        for (int q = 0; q < 3; ++q) p.push_lo[q] = p.push_hi[q] = nullptr;
+        p.edge_b = -1; p.zface = 0; p.ztile0 = 0;
+        p.zf_cl = p.zf_ct = (T)0;
+        p.g = geo();
+        p.cur = fld(b_cur()); p.old = fld(b_old()); p.nw = fld(b_new());
+        p.line_save = (c->w && c->cfg.x0 == 0) ? (const T *)c->line_save : nullptr;
+        p.i_begin = ib; p.i_end = ie;
+        MatCls<T> m = mat();
+        dim3 bl = block_for(c->cfg.nz), gr = grid3(c->cfg.nz, ie - ib, 1, bl);
+        if (c->cfg.arith == PHB_EXACT) k_pbc_y<Ar<T, true>, MatCls<T>><<<gr, bl, 0, c->st>>>(p, m);
+        else k_pbc_y<Ar<T, false>, MatCls<T>><<<gr, bl, 0, c->st>>>(p, m);
+        c->launches++;
+        CU(cudaGetLastError());
+        return 0;
+    }
     int abc_yz(int ib, int ie) {
         if (ie <= ib) return 0;
         AbcArgs<T> a = abc_args(ib, ie);
-        a.z_edges_only = (use_march() && zface_fused()) ? 1 : 0;
-        {
+        a.z_edges_only = (use_march() && zface_fused() && !getenv("PHB_DEBUG_ZF_NOP")) ? 1 : 0;
+        if (!periodic_y()) {
             dim3 bl = block_for(c->cfg.nz), gr = grid3(c->cfg.nz, ie - ib, 1, bl);
             gr.z = 2;
             if (c->cfg.arith == PHB_EXACT) k_abc_y<Ar<T, true>><<<gr, bl, 0, c->st>>>(a);
@@ -609,7 +657,7 @@ struct Engine : IEngine {
             else if (comp()) k_abc_z<Ar<T, false, true>><<<gr, bl, 0, c->st>>>(a);
             else k_abc_z<Ar<T, false>><<<gr, bl, 0, c->st>>>(a);
         }
-        c->launches += 2;
+        c->launches += periodic_y() ? 1 : 2;
         CU(cudaGetLastError());
         return 0;
     }
@@ -707,6 +755,7 @@ struct Engine : IEngine {
             // absorbing faces are applied to the owned planes AND to the received ghost planes (same formula and
             // inputs as on the owning rank, so the result stays bit-identical).
             if (!use_march()) return fail("halo=p2p needs the marching kernel");
+            if (periodic_y()) return fail("periodic y boundaries need the NCCL halo path (the fix-up rows are final only after the stencil kernel)");
             const bool hasL = c->rank > 0, hasR = c->rank < c->nranks - 1;
             OK(physics(x0, xe));
             const int stepno = (int)(c->tt + 1);
@@ -725,23 +774,27 @@ struct Engine : IEngine {
             int ib = x0, ie = xe;
             if (hasL && hasR && use_march()) {
                 OK(physics(x0, x0 + 1, xe - 1));      // both edge planes in one launch
+                OK(pbc_y(x0, x0 + 1));
+                OK(pbc_y(xe - 1, xe));
                 OK(abc_yz(x0, x0 + 1));
                 OK(abc_yz(xe - 1, xe));
                 ib = x0 + 1; ie = xe - 1;
             } else {
-                if (hasL) { OK(physics(x0, x0 + 1)); OK(abc_yz(x0, x0 + 1)); ib = x0 + 1; }
-                if (hasR) { OK(physics(xe - 1, xe)); OK(abc_yz(xe - 1, xe)); ie = xe - 1; }
+                if (hasL) { OK(physics(x0, x0 + 1)); OK(pbc_y(x0, x0 + 1)); OK(abc_yz(x0, x0 + 1)); ib = x0 + 1; }
+                if (hasR) { OK(physics(xe - 1, xe)); OK(pbc_y(xe - 1, xe)); OK(abc_yz(xe - 1, xe)); ie = xe - 1; }
             }
             CU(cudaEventRecord(c->ev_edge, c->st));
             CU(cudaStreamWaitEvent(c->cst, c->ev_edge, 0));
             if (c->comm) OK(exchange());
             CU(cudaEventRecord(c->ev_comm, c->cst));
             OK(physics(ib, ie));
+            OK(pbc_y(ib, ie));
             if (last) OK(abc_x());
             OK(abc_yz(ib, ie));
             CU(cudaStreamWaitEvent(c->st, c->ev_comm, 0));
         } else {
             OK(physics(x0, xe));
+            OK(pbc_y(x0, xe));
             if (last) OK(abc_x());
             OK(abc_yz(x0, xe));
         }
@@ -884,6 +937,8 @@ int phb_create(const phb_cfg *cfg, phb_ctx **out) {
     if (cfg->x0 < 0 || cfg->nxl < 1 || cfg->x0 + cfg->nxl > cfg->nx) return fail("bad slab [%d, %d) of %d", cfg->x0, cfg->x0 + cfg->nxl, cfg->nx);
     if (cfg->dtype != PHB_F32 && cfg->dtype != PHB_F64) return fail("bad dtype %d", cfg->dtype);
     if (cfg->arith != PHB_FAST && cfg->arith != PHB_EXACT && cfg->arith != PHB_COMP) return fail("bad arith %d", cfg->arith);
+    if (cfg->bc_y != PHB_BC_ABSORBING && cfg->bc_y != PHB_BC_PERIODIC) return fail("bad bc_y %d", cfg->bc_y);
+    if (cfg->bc_y == PHB_BC_PERIODIC && cfg->arith == PHB_COMP) return fail("periodic y boundaries are not available with the compensated state");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
@@ -908,6 +963,14 @@ int phb_create(const phb_cfg *cfg, phb_ctx **out) {
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
         if (cudaStreamCreateWithPriority(&c->cst, cudaStreamNonBlocking, hi) != cudaSuccess) return cleanup(fail("stream create failed"));
     }
+    {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (cudaStreamCreateWithPriority(&c->zst, cudaStreamNonBlocking, hi) != cudaSuccess) return cleanup(fail("stream create failed"));
+    }
+    cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
+    if (const char *e = getenv("PHB_ZSPLIT")) c->zsplit = atoi(e) != 0;
     cudaEventCreateWithFlags(&c->ev_edge, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->ev_comm, cudaEventDisableTiming);
     cudaEventCreate(&c->ev_t0);
@@ -988,6 +1051,9 @@ int phb_destroy(phb_ctx *c) {
     cudaFree(c->ring_dev);
     for (auto &pr : c->probes) cudaFree(pr.trace);
     for (auto &pe : c->prof_ev) { cudaEventDestroy(pe.first); cudaEventDestroy(pe.second); }
+    if (c->zst) { cudaStreamSynchronize(c->zst); cudaStreamDestroy(c->zst); }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->ev_edge) cudaEventDestroy(c->ev_edge);
     if (c->ev_comm) cudaEventDestroy(c->ev_comm);
     if (c->ev_t0) cudaEventDestroy(c->ev_t0);
@@ -1341,6 +1407,7 @@ int phb_p2p_import(phb_ctx *c, int32_t rank, int32_t nranks, const char *left, i
     graph_invalidate(c);
     if (nranks < 1 || rank < 0 || rank >= nranks) return fail("bad rank %d of %d", rank, nranks);
     if (!c->flags) return fail("call phb_p2p_export first");
+    if (c->cfg.bc_y == PHB_BC_PERIODIC) return fail("periodic y boundaries: use the NCCL halo path (phb_comm_init)");
     c->rank = rank; c->nranks = nranks;
     if (nranks == 1) return 0;
     if (c->cfg.nxl < 4) return fail("a slab needs at least 4 planes (got %d)", c->cfg.nxl);

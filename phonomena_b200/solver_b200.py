@@ -54,6 +54,8 @@ cfg = {
     "material": "inclusions",   # "inclusions": primary/secondary + inclusion list, filled on the device (what Material.update
                                 # builds) | "arrays": take material.C / material.P as they are (any <= 15 distinct cells)
     "merge_slabs": True,        # multi-GPU: concatenate the per-slab files into `file` after the run (rank 0)
+    "bc_y": "absorbing",        # "absorbing": Mur faces at y = 0 / y = -1 (the reference) | "periodic": the reference's archived
+                                # apply_T_pbc / apply_u_pbc stubs (zero Bloch phase) in their place
     "probes": [],               # [{"u": "uz", "y": j, "z": k}, ...]: (x, t) lines kept on the device for Solver.spectrum()
 }
 
@@ -240,7 +242,8 @@ class Solver:
         e = _lib.Engine(x.size, y.size, z.size, dt, d2=dt ** 2,
                         dtype={"fp64": "f64", "fp32": "f32"}[c["precision"]], arith=c["arith"],
                         device=int(c["device"]), x0=x0, nxl=nxl, kernel=c.get("kernel", "auto"),
-                        record_mask=rec_mask, record_every=int(c["record_every"]), ring_slots=ring_slots)
+                        record_mask=rec_mask, record_every=int(c["record_every"]), ring_slots=ring_slots,
+                        bc_y=c.get("bc_y", "absorbing"))
         self.engine = e
         if nranks > 1:
             # one process per GPU: fused NVLink halo push (CUDA IPC handles all-gathered over any host channel,

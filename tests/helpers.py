@@ -13,7 +13,13 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 def golden_names():
     """Solver fixtures (the spectrum_* fixtures have their own layout, tests/test_spectrum_cpu.py)."""
     names = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
-    return [n for n in names if not n.startswith("spectrum_")]
+    return [n for n in names if not n.startswith(("spectrum_", "periodic_y_"))]
+
+
+def periodic_names():
+    """Fixtures made with the reference's archived periodic-y stubs switched on (oracle/gen_golden.periodic_y_solver)."""
+    names = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    return [n for n in names if n.startswith("periodic_y_")]
 
 
 def load_golden(name):
@@ -32,13 +38,13 @@ def targets_of(d):
     return onp.make_targets(d["targets"].tolist()) if d["targets"].size else onp.make_targets([])
 
 
-def oracle_from_golden(d, threads=1):
+def oracle_from_golden(d, threads=1, **kw):
     """Oracle solver built ONLY from the fixture's inputs (mesh lines, inclusions, tables)."""
     t = targets_of(d)
     C, P = onp.set_constants(d["x"], d["y"], d["z"], t, d["prim_c"], d["prim_p"], d["sec_c"], d["sec_p"])
     fdx, fdy, fdz, *_ = onp.spacings(d["x"], d["y"], d["z"])
     dt = onp.cfl_time_step(fdx, fdy, fdz, d["courant"], d["prim_c"], d["prim_p"], d["sec_c"], d["sec_p"])
-    return onp.OracleSolver(d["x"], d["y"], d["z"], C, P, dt, wave=d["wave"], wave_args=d["wave_args"], threads=threads)
+    return onp.OracleSolver(d["x"], d["y"], d["z"], C, P, dt, wave=d["wave"], wave_args=d["wave_args"], threads=threads, **kw)
 
 
 def rel_l2(a, b):

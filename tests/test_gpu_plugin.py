@@ -300,7 +300,7 @@ def test_plugin_reinit_without_run_and_cancel_latency(tmp_path):
     assert H5Reader(first).attrs["frames_written"] == 0
     s.run()
     assert H5Reader(s.file).attrs["frames_written"] == 30
-    s2 = make_solver(d, tmp_path, write_mode="off", chunk_steps=10_000_000)
+    s2 = make_solver(d, tmp_path, write_mode="off", chunk_steps=100_000)       # (the host evaluates a chunk's source samples first: 2 us each)
     s2.init(*fake_from_golden(d), 10_000_000)
     th = threading.Thread(target=s2.run)
     th.start()

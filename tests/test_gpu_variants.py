@@ -1,5 +1,6 @@
 """Every configuration of the marching kernel gives the reference's bits: one / two rows per warp
-(PHB_MARCH_RW), the z = -1 absorbing face inside the stencil kernel or as its own kernel (PHB_ZFUSE),
+(PHB_MARCH_RW), the z = -1 absorbing face inside the stencil kernel or as its own kernel (PHB_ZFUSE), the
+step split into a launch for the face-owning z-tile beside one for the others or not (PHB_ZSPLIT),
 several z-tiles, y-tiles and x-chunks, grids whose nz makes the fused face possible (nz a multiple of
 the vector width) and grids where the host must fall back to the separate face kernel.  fp64 EXACT
 arithmetic is compared bit for bit with the C oracle (which follows base_solver.py:245-260, 323-571);
@@ -17,6 +18,8 @@ VARIANTS = [
     {"PHB_MARCH_RW": "2", "PHB_ZFUSE": "0"},
     {"PHB_MARCH_RW": "1"},
     {"PHB_MARCH_RW": "2", "PHB_ZFUSE": "1", "PHB_MARCH_CHUNKS": "3"},
+    {"PHB_MARCH_RW": "2", "PHB_ZFUSE": "1", "PHB_ZSPLIT": "0"},      # fused face, one launch for all z-tiles (default: split step)
+    {"PHB_MARCH_RW": "2", "PHB_ZFUSE": "1", "PHB_GRAPH": "0"},
 ]
 SHAPES = [
     ((24, 33, 128), 9),      # fp64: 2 z-tiles, face in the last lane of the second; 3 y-tiles
@@ -24,6 +27,7 @@ SHAPES = [
     ((40, 17, 64), 11),      # exactly one fp64 z-tile
     ((12, 30, 66), 7),       # fp64: nz - 1 = 65 sits in lane 0 of the second tile -> host keeps the face kernel
     ((16, 16, 35), 7),       # nz odd -> no fusion in either precision
+    ((14, 20, 200), 12),     # fp64: 4 z-tiles (split step: 3 + 1), fp32: 2; enough steps for the CUDA-graph replay of the split
 ]
 
 

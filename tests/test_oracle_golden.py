@@ -123,3 +123,27 @@ def test_c_oracle_bit_exact(name, omp):
     for k in ("ux", "uy", "uz", "ux_old", "uy_old", "uz_old", "T1", "T2", "T3", "T4", "T5", "T6"):
         assert np.array_equal(getattr(o, k), d[k]), (name, k)
     o.close()
+
+
+@pytest.mark.parametrize("name", H.periodic_names())
+def test_periodic_y_oracle_matches_reference_stubs(name):
+    """bc_y = periodic: the oracle's restatement of the reference's ARCHIVED apply_T_pbc / apply_u_pbc
+    (base_solver.py:383-400, 475-486) against fixtures made by the unmodified reference solver with those stubs
+    switched on through its own update_T_BC / update_u_BC hooks (oracle/gen_golden.periodic_y_solver) -- bit for bit,
+    stresses included."""
+    d = H.load_golden(name)
+    assert str(d["bc_y"]) == "periodic"
+    o = H.oracle_from_golden(d, bc_y="periodic")
+    assert o.dt == d["dt"]
+    snaps = set(int(s) for s in d["snap_steps"])
+    for n in range(1, d["steps"] + 1):
+        o.step()
+        if n in snaps:
+            assert np.array_equal(o.uz[:, :, 0], d["snap_uz_%d" % n]) and np.array_equal(o.ux[:, :, 0], d["snap_ux_%d" % n]), (name, n)
+    for k in ("ux", "uy", "uz", "ux_old", "uy_old", "uz_old", "T1", "T2", "T3", "T4", "T5", "T6"):
+        assert np.array_equal(getattr(o, k), d[k]), (name, k)
+    # the mode does something: the absorbing oracle on the same inputs ends elsewhere, and the periodic rows are copies
+    a = H.oracle_from_golden(d).run(d["steps"])
+    assert not np.array_equal(a.uz, o.uz)
+    assert np.array_equal(o.ux[:, 0, :-1], o.ux[:, -2, :-1]) and np.array_equal(o.uy[:, -1, :-1], o.uy[:, 1, :-1])
+    assert np.array_equal(o.uz[:, 0, :-1], o.uz[:, -2, :-1])
