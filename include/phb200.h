@@ -74,7 +74,9 @@ typedef struct phb_cfg {
     int32_t record_every;    /* record the k=0 plane after every n-th step (>=1)                  */
     int32_t ring_slots;      /* pinned-host ring depth (frames); 0 = default                      */
     int32_t bc_y;            /* PHB_BC_ABSORBING (0, the reference's behaviour) | PHB_BC_PERIODIC                */
-    int32_t reserved[3];
+    int32_t record_stride[3]; /* PHB_REC_FULL only: keep every sx-th plane / sy-th row / sz-th level (global indices that
+                                * are multiples of the stride; 0 = 1).  A decimated full-volume snapshot of a large grid
+                                * fits the recorder ring where the whole arrays would not; a slab needs x0 % sx == 0. */
     double  dt;              /* material.dt                                      (material.py:80-93) */
     double  d2;              /* dt**2 as evaluated by the host (base_solver.py:443: self.m.dt**2) */
 } phb_cfg;

@@ -47,7 +47,7 @@ class Cfg(C.Structure):
         ("x0", C.c_int32), ("nxl", C.c_int32),
         ("dtype", C.c_int32), ("arith", C.c_int32), ("device", C.c_int32), ("kernel", C.c_int32),
         ("record_mask", C.c_int32), ("record_every", C.c_int32), ("ring_slots", C.c_int32),
-        ("bc_y", C.c_int32), ("reserved", C.c_int32 * 3),
+        ("bc_y", C.c_int32), ("record_stride", C.c_int32 * 3),
         ("dt", C.c_double), ("d2", C.c_double),
     ]
 
@@ -165,7 +165,7 @@ class Engine:
     """One device context = one grid or one x-slab [x0, x0+nxl) on one GPU."""
 
     def __init__(self, nx, ny, nz, dt, d2=None, dtype="f64", arith="fast", device=0, x0=0, nxl=None,
-                 kernel="auto", record_mask=0, record_every=1, ring_slots=0, bc_y="absorbing"):
+                 kernel="auto", record_mask=0, record_every=1, ring_slots=0, bc_y="absorbing", record_stride=(1, 1, 1)):
         self.lib = load_library()
         self.nx, self.ny, self.nz = int(nx), int(ny), int(nz)
         self.x0 = int(x0)
@@ -177,6 +177,9 @@ class Engine:
         cfg.dtype, cfg.arith, cfg.device = self.dtype, self.arith, int(device)
         cfg.kernel = {"auto": KERNEL_AUTO, "naive": KERNEL_NAIVE, "march": KERNEL_MARCH}[kernel]
         cfg.record_mask, cfg.record_every, cfg.ring_slots = int(record_mask), int(record_every), int(ring_slots)
+        self.record_stride = tuple(max(1, int(v)) for v in record_stride) if (int(record_mask) & REC_FULL) else (1, 1, 1)
+        for q in range(3):
+            cfg.record_stride[q] = self.record_stride[q]
         cfg.bc_y = {"absorbing": BC_ABSORBING, "periodic": BC_PERIODIC}[bc_y]
         self.bc_y = bc_y
         cfg.dt = float(dt)
@@ -382,13 +385,15 @@ class Engine:
     def frame_layout(self):
         """[(name, shape)] of the recorded components inside one frame."""
         out = []
-        full = bool(self.record_mask & REC_FULL)      # whole arrays instead of their k = 0 planes
+        full = bool(self.record_mask & REC_FULL)      # whole arrays (every record_stride-th entry) instead of their k = 0 planes
+        sx, sy, sz = self.record_stride
+        cd = lambda n, s: -(-n // s)
         if self.record_mask & REC_UX:
-            out.append(("ux", (self.planes(0), self.ny) + ((self.nz,) if full else ())))
+            out.append(("ux", (cd(self.planes(0), sx), cd(self.ny, sy), cd(self.nz, sz)) if full else (self.planes(0), self.ny)))
         if self.record_mask & REC_UY:
-            out.append(("uy", (self.nxl, self.ny - 1) + ((self.nz,) if full else ())))
+            out.append(("uy", (cd(self.nxl, sx), cd(self.ny - 1, sy), cd(self.nz, sz)) if full else (self.nxl, self.ny - 1)))
         if self.record_mask & REC_UZ:
-            out.append(("uz", (self.nxl, self.ny) + ((self.nz - 1,) if full else ())))
+            out.append(("uz", (cd(self.nxl, sx), cd(self.ny, sy), cd(self.nz - 1, sz)) if full else (self.nxl, self.ny)))
         return out
 
     def record_next(self, timeout_ms=1000):

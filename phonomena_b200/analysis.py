@@ -7,36 +7,7 @@ from __future__ import annotations
 import numpy as np
 
 from .h5lite import H5Reader
-
-
-def nonlinspace(spacing):
-    """analysis.py:9-18: cumulative positions from a spacing array (first spacing skipped)."""
-    spacing = np.asarray(spacing, np.float64)
-    if spacing.ndim > 1:
-        raise TypeError("Only supports 1D arrays")
-    X = np.zeros(spacing.size)
-    for i in range(1, len(spacing)):
-        X[i] = X[i - 1] + spacing[i]
-    return X
-
-
-def trim_trailing_zeros(arr, threshold=1):
-    """analysis.py:19-42."""
-    og = np.copy(arr)
-    arr[arr < (threshold * np.max(arr) / 100)] = 0
-    if arr.ndim == 1:
-        out = np.trim_zeros(arr, "b")
-        if out.size == 0:
-            out = og
-        return out, range(0, out.size)
-    if arr.ndim == 2:
-        flat = np.prod(arr, axis=0)
-        tmp = np.trim_zeros(flat, "b")
-        if tmp.size == 0:
-            tmp = flat
-        idx = range(0, tmp.size)
-        return arr[:, idx], idx
-    raise TypeError("Only accepts 1D arrays")
+from .hostmath import nonlinspace
 
 
 def spectrum(file, u_id, z_index, y_index, x_index=None):

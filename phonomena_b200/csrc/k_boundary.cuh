@@ -121,11 +121,23 @@ __global__ void k_abc_z(AbcArgs<typename A::T> p) {
 // Fused halo push: after the stencil kernel has stored the edge planes into the neighbours' ghost
 // planes, tell them which step is complete (flags live in the NEIGHBOUR's memory, CUDA IPC).
 // ---------------------------------------------------------------------------------------
-__global__ void k_signal(volatile int *left_flag, volatile int *right_flag, int step) {
+// The step number is not a launch argument: both kernels read the count of completed steps from device memory and the
+// wait kernel advances it, so the whole slab step can be replayed as a CUDA graph (phb200.cu step()).
+__global__ void k_signal(volatile int *left_flag, volatile int *right_flag, const int *steps_done) {
+    const int step = *steps_done + 1;
     __threadfence_system();
     if (left_flag) *left_flag = step;
     if (right_flag) *right_flag = step;
     __threadfence_system();
+}
+// Wait until both neighbours have signalled this step (their edge planes sit in my ghost planes), then count the step.
+// One thread; it runs after the stencil launch of the step has completed (stream order), so it takes no SM from it.
+__global__ void k_wait_flags(const volatile int *from_left, const volatile int *from_right, int *steps_done) {
+    const int step = *steps_done + 1;
+    if (from_left) while (*from_left < step) __nanosleep(40);
+    if (from_right) while (*from_right < step) __nanosleep(40);
+    __threadfence_system();
+    *steps_done = step;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -147,6 +159,16 @@ __global__ void k_gather(const T *src, double *dst, int np, int ey, int ez, int 
     const int p = blockIdx.z;
     if (k >= ez || j >= ey || p >= np) return;
     dst[((long long)p * ey + j) * ez + k] = (double)src[((long long)(l0 + p) * ny + j) * nzp + k];
+}
+
+// decimated gather (PHB_REC_FULL with record_stride): dst (npd, eyd, ezd) <- every (sx, sy, sz)-th entry
+template <class T>
+__global__ void k_gather_strided(const T *src, double *dst, int npd, int eyd, int ezd, int l0, int ny, int nzp, int sx, int sy, int sz) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    const int p = blockIdx.z;
+    if (k >= ezd || j >= eyd || p >= npd) return;
+    dst[((long long)p * eyd + j) * ezd + k] = (double)src[((long long)(l0 + p * sx) * ny + (long long)j * sy) * nzp + (long long)k * sz];
 }
 
 // COMP state: the `old` slot holds delta = u - u_old.  Host-side "u_old" <-> device delta.

@@ -146,7 +146,8 @@ __global__ void __launch_bounds__(256) k_pbc_y(StepArgs<typename A::T> p, M m) {
     }
     if (k <= g.nz - 2) {
         p.nw.uz[r0] = p.nw.uz[rm];
-        p.nw.uz[rl] = p.cur.uz[rl];
+        // (the source line of the current field is not part of u_new: the pre-source value is, App. B #9)
+        p.nw.uz[rl] = (i == 0 && k == 0 && p.line_save) ? p.line_save[g.ny - 1] : p.cur.uz[rl];
     }
     p.nw.uy[rm] = p.nw.uy[r1];
 }

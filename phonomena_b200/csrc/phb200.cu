@@ -159,7 +159,7 @@ struct phb_ctx {
     int halo = 0;
     void *peer_buf[2][3] = {};   // [left | right][buffer]: the neighbour's displacement buffers, mapped
     int peer_nxl[2] = {0, 0};
-    int *flags = nullptr;        // [0] written by the left neighbour, [1] by the right one: last step pushed
+    int *flags = nullptr;        // [0] written by the left neighbour, [1] by the right one: last step pushed; [8] = steps done (k_wait_flags)
     int *peer_flags[2] = {};     // the neighbours' flag arrays, mapped
     // recorder: pinned host ring (rec_ring.h) filled through a device staging ring; drained by the native writer
     // threads (phb_writer_start) or by the caller (phb_record_next / phb_record_release)
@@ -662,21 +662,6 @@ struct Engine : IEngine {
         return 0;
     }
 
-    int wait_flag(int *flag, int value) {
-        typedef CUresult (*PFN_wait)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
-        static PFN_wait fn = nullptr;
-        if (!fn) {
-            void *q = nullptr;
-            cudaDriverEntryPointQueryResult qres;
-            if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &q, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess)
-                return fail("cuStreamWaitValue32 not available");
-            fn = (PFN_wait)q;
-        }
-        if (fn((CUstream)c->st, (CUdeviceptr)flag, (cuuint32_t)value, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
-            return fail("cuStreamWaitValue32 failed");
-        return 0;
-    }
-
     int exchange() {
         // send new[x0] to the left neighbour (its right ghost), new[x0+nxl-1] to the right
         // neighbour (its left ghost); receive the mirror images.  3 components per direction.
@@ -704,7 +689,9 @@ struct Engine : IEngine {
         if (c->w && c->cfg.x0 == 0 && c->tt - c->w_base >= c->nw)
             return fail("source table covers steps %lld..%lld, step %lld requested", c->w_base, c->w_base + c->nw - 1, c->tt);
         // single GPU: replay the step as a CUDA graph (captured per rotation phase after a few plain steps)
-        const bool graphable = c->graph_mode && c->nranks == 1 && !c->prof;
+        // (slabs too when the halos are pushed from inside the stencil kernel: the flag kernels take the step number from
+        // device memory; the NCCL path is launched call by call)
+        const bool graphable = c->graph_mode && (c->nranks == 1 || c->halo == 2) && !c->prof;
         if (graphable && c->plain_steps >= 3) {
             const int ph = c->cur;
             if (!c->gexec[ph]) {
@@ -758,11 +745,9 @@ struct Engine : IEngine {
             if (periodic_y()) return fail("periodic y boundaries need the NCCL halo path (the fix-up rows are final only after the stencil kernel)");
             const bool hasL = c->rank > 0, hasR = c->rank < c->nranks - 1;
             OK(physics(x0, xe));
-            const int stepno = (int)(c->tt + 1);
-            k_signal<<<1, 1, 0, c->st>>>(hasL ? c->peer_flags[0] + 1 : nullptr, hasR ? c->peer_flags[1] + 0 : nullptr, stepno);
-            c->launches++;
-            if (hasL) OK(wait_flag(c->flags + 0, stepno));
-            if (hasR) OK(wait_flag(c->flags + 1, stepno));
+            k_signal<<<1, 1, 0, c->st>>>(hasL ? c->peer_flags[0] + 1 : nullptr, hasR ? c->peer_flags[1] + 0 : nullptr, c->flags + 8);
+            k_wait_flags<<<1, 1, 0, c->st>>>(hasL ? c->flags + 0 : nullptr, hasR ? c->flags + 1 : nullptr, c->flags + 8);
+            c->launches += 2;
             if (last) OK(abc_x());
             OK(abc_yz(x0 - (hasL ? 1 : 0), xe + (hasR ? 1 : 0)));
             return 0;
@@ -819,19 +804,26 @@ static int record_frame(phb_ctx *c) {
     double *slot = c->ring_dev + (long long)s * c->rec.frame_doubles;
     const int npx = std::max(0, std::min(c->cfg.x0 + c->cfg.nxl, c->cfg.nx - 1) - c->cfg.x0), npyz = c->cfg.nxl;
     if (c->cfg.record_mask & PHB_REC_FULL) {
-        // whole arrays in the reference's shapes, one coalesced gather per component (the kernel get_fields uses)
+        // whole arrays in the reference's shapes (or every (sx, sy, sz)-th entry of them), one gather per component
         const int ny = c->cfg.ny, nz = c->cfg.nz;
+        const int sx = c->cfg.record_stride[0], sy = c->cfg.record_stride[1], sz = c->cfg.record_stride[2];
         const int np[3] = {npx, npyz, npyz}, ey[3] = {ny, ny - 1, ny}, ez[3] = {nz, nz, nz - 1};
         double *o = slot;
         for (int comp = 0; comp < 3; ++comp) {
             if (!(c->cfg.record_mask & (1 << comp))) continue;
-            const long long cnt = (long long)np[comp] * ey[comp] * ez[comp];
+            const int npd = (np[comp] + sx - 1) / sx, eyd = (ey[comp] + sy - 1) / sy, ezd = (ez[comp] + sz - 1) / sz;
+            const long long cnt = (long long)npd * eyd * ezd;
             if (cnt > 0) {
-                dim3 bl = block_for(ez[comp]), gr = grid3(ez[comp], ey[comp], np[comp], bl);
-                if (c->cfg.dtype == PHB_F64)
-                    k_gather<double><<<gr, bl, 0, c->st>>>((const double *)c->buf[c->cur][comp], o, np[comp], ey[comp], ez[comp], 1, ny, c->nzp);
+                dim3 bl = block_for(ezd), gr = grid3(ezd, eyd, npd, bl);
+                if (sx == 1 && sy == 1 && sz == 1) {
+                    if (c->cfg.dtype == PHB_F64)
+                        k_gather<double><<<gr, bl, 0, c->st>>>((const double *)c->buf[c->cur][comp], o, np[comp], ey[comp], ez[comp], 1, ny, c->nzp);
+                    else
+                        k_gather<float><<<gr, bl, 0, c->st>>>((const float *)c->buf[c->cur][comp], o, np[comp], ey[comp], ez[comp], 1, ny, c->nzp);
+                } else if (c->cfg.dtype == PHB_F64)
+                    k_gather_strided<double><<<gr, bl, 0, c->st>>>((const double *)c->buf[c->cur][comp], o, npd, eyd, ezd, 1, ny, c->nzp, sx, sy, sz);
                 else
-                    k_gather<float><<<gr, bl, 0, c->st>>>((const float *)c->buf[c->cur][comp], o, np[comp], ey[comp], ez[comp], 1, ny, c->nzp);
+                    k_gather_strided<float><<<gr, bl, 0, c->st>>>((const float *)c->buf[c->cur][comp], o, npd, eyd, ezd, 1, ny, c->nzp, sx, sy, sz);
                 c->launches++;
             }
             o += cnt;
@@ -999,9 +991,13 @@ int phb_create(const phb_cfg *cfg, phb_ctx **out) {
         const int npx = std::max(0, std::min(cfg->x0 + cfg->nxl, cfg->nx - 1) - cfg->x0);
         long long fd = 0;
         const bool full = (cfg->record_mask & PHB_REC_FULL) != 0;      // whole arrays: Grid.freezeData (grid.py:68-77)
-        if (cfg->record_mask & PHB_REC_UX) fd += (long long)npx * cfg->ny * (full ? cfg->nz : 1);
-        if (cfg->record_mask & PHB_REC_UY) fd += (long long)cfg->nxl * (cfg->ny - 1) * (full ? cfg->nz : 1);
-        if (cfg->record_mask & PHB_REC_UZ) fd += (long long)cfg->nxl * cfg->ny * (full ? cfg->nz - 1 : 1);
+        int *rs = c->cfg.record_stride;
+        for (int q = 0; q < 3; ++q) if (rs[q] < 1 || !full) rs[q] = 1;
+        if (cfg->x0 % rs[0] != 0) return cleanup(fail("record_stride[0] = %d does not divide the slab origin x0 = %d", rs[0], cfg->x0));
+        auto cd = [](long long n, int s) { return (n + s - 1) / s; };
+        if (cfg->record_mask & PHB_REC_UX) fd += full ? cd(npx, rs[0]) * cd(cfg->ny, rs[1]) * cd(cfg->nz, rs[2]) : (long long)npx * cfg->ny;
+        if (cfg->record_mask & PHB_REC_UY) fd += full ? cd(cfg->nxl, rs[0]) * cd(cfg->ny - 1, rs[1]) * cd(cfg->nz, rs[2]) : (long long)cfg->nxl * (cfg->ny - 1);
+        if (cfg->record_mask & PHB_REC_UZ) fd += full ? cd(cfg->nxl, rs[0]) * cd(cfg->ny, rs[1]) * cd(cfg->nz - 1, rs[2]) : (long long)cfg->nxl * cfg->ny;
         if (fd <= 0) return cleanup(fail("record_mask %d selects no component", cfg->record_mask));
         c->rec.frame_doubles = fd;
         c->rec.slots = cfg->ring_slots > 0 ? cfg->ring_slots : 16;
@@ -1423,6 +1419,11 @@ int phb_p2p_import(phb_ctx *c, int32_t rank, int32_t nranks, const char *left, i
         memcpy(&h, src[s] + 192, 64);
         CU(cudaIpcOpenMemHandle((void **)&c->peer_flags[s], h, cudaIpcMemLazyEnablePeerAccess));
         c->peer_nxl[s] = nx2[s];
+    }
+    {   // the flag kernels count steps in device memory from what has been run so far
+        const int done = (int)c->tt;
+        CU(cudaMemcpyAsync(c->flags + 8, &done, sizeof(int), cudaMemcpyHostToDevice, c->st));
+        CU(cudaStreamSynchronize(c->st));
     }
     c->halo = 2;
     return 0;

@@ -53,6 +53,7 @@ cfg = {
     "kernel": "auto",
     "material": "inclusions",   # "inclusions": primary/secondary + inclusion list, filled on the device (what Material.update
                                 # builds) | "arrays": take material.C / material.P as they are (any <= 15 distinct cells)
+    "record_stride": [1, 1, 1], # record = "full": keep every sx-th plane / sy-th row / sz-th level (decimated volume snapshots of big grids)
     "merge_slabs": True,        # multi-GPU: concatenate the per-slab files into `file` after the run (rank 0)
     "bc_y": "absorbing",        # "absorbing": Mur faces at y = 0 / y = -1 (the reference) | "periodic": the reference's archived
                                 # apply_T_pbc / apply_u_pbc stubs (zero Bloch phase) in their place
@@ -88,8 +89,9 @@ class Writer:
     WRITE_THREADS = 4      # native threads, each writes whole frames
     PREALLOCATE_MAX_BYTES = 2 << 30
 
-    def __init__(self, path, engine, meta, frames, mode, record_every, ring=True, fields=("ux", "uy", "uz")):
+    def __init__(self, path, engine, meta, frames, mode, record_every, ring=True, fields=("ux", "uy", "uz"), stride=(1, 1, 1)):
         self.path, self.e, self.mode, self.frames = path, engine, mode, frames
+        self.stride = tuple(stride) if mode == "full" else (1, 1, 1)
         self.ring = ring or mode == "surface"      # frames arrive through the device / pinned ring (else: put_full)
         self.h5 = H5Writer(path)
         self.h5.attrs.update(meta["attrs"])
@@ -101,8 +103,11 @@ class Writer:
         ny, nz = engine.ny, engine.nz
         zext = 1 if mode == "surface" else None
         # x extents are the planes this context owns (the whole grid, or one slab: attrs x0 / nxl)
-        shapes = {"ux": (engine.planes(0), ny, zext or nz, frames), "uy": (engine.planes(1), ny - 1, zext or nz, frames),
-                  "uz": (engine.planes(2), ny, zext or (nz - 1), frames)}
+        cd = lambda n, s: -(-n // s)
+        sx, sy, sz = self.stride
+        shapes = {"ux": (cd(engine.planes(0), sx), cd(ny, sy), zext or cd(nz, sz), frames),
+                  "uy": (cd(engine.planes(1), sx), cd(ny - 1, sy), zext or cd(nz, sz), frames),
+                  "uz": (cd(engine.planes(2), sx), cd(ny, sy), zext or cd(nz - 1, sz), frames)}
         self.ds = {k: self.h5.create_chunked(k, shapes[k]) for k in ("ux", "uy", "uz") if k in fields}
         # The static datasets (density alone is Nx*Ny*Nz doubles) are pushed out now, in init(), like the reference's
         # Writer.init (base_solver.py:105-133): otherwise the kernel's dirty-page writeback of them throttles the
@@ -129,9 +134,10 @@ class Writer:
 
     # full mode without a ring: called synchronously by the run loop
     def put_full(self, fields):
+        sx, sy, sz = self.stride
         for name, a in zip(("ux", "uy", "uz"), fields):
             if name in self.ds:
-                self.h5.write_frame(self.ds[name], self.written, a)
+                self.h5.write_frame(self.ds[name], self.written, a[::sx, ::sy, ::sz])
         self.written += 1
 
     def finish(self, timeout=300.0):
@@ -169,7 +175,8 @@ class Writer:
 
 
 class Solver:
-    FULL_RING_MAX_FRAME_BYTES = 64 << 20     # record = "full": frames up to this size stream through the recorder ring
+    FULL_RING_MAX_FRAME_BYTES = 1 << 30      # record = "full": frames up to this size stream through the recorder ring
+    FULL_RING_BYTES = 2 << 30                # pinned + device staging ring budget for them (>= 2 slots)
 
     def __init__(self):
         self.name = "b200"
@@ -234,16 +241,25 @@ class Solver:
             # whole arrays every recorded step (the reference's Writer, base_solver.py:97-100,135-160): when a frame is
             # small enough they go through the same device ring -> pinned ring -> writer thread as the surface planes,
             # so the stepping loop never waits for a read-back; big grids keep the synchronous get_fields path
-            fbytes = 8 * nxl * y.size * z.size * len(fields)
+            # (cfg["record_stride"] decimates the volume: 512^3 at stride 4 is a 50 MB frame instead of 3.2 GB)
+            stride = tuple(max(1, int(v)) for v in (list(c.get("record_stride") or [1, 1, 1]) + [1, 1, 1])[:3])
+            if x0 % stride[0]:
+                raise ValueError("record_stride[0] = %d does not divide this slab's origin x0 = %d" % (stride[0], x0))
+            fbytes = 8 * -(-nxl // stride[0]) * -(-y.size // stride[1]) * -(-z.size // stride[2]) * len(fields)
             if fbytes <= self.FULL_RING_MAX_FRAME_BYTES:
                 rec_mask = fmask | _lib.REC_FULL
-                ring_slots = int(max(4, min(32, (256 << 20) // max(1, fbytes))))
+                ring_slots = int(max(2, min(32, self.FULL_RING_BYTES // max(1, fbytes))))
+        else:
+            stride = (1, 1, 1)
+        if rec_mode != "full":
+            stride = (1, 1, 1)
+        self._stride = stride
         self._full_ring = bool(rec_mask & _lib.REC_FULL)
         e = _lib.Engine(x.size, y.size, z.size, dt, d2=dt ** 2,
                         dtype={"fp64": "f64", "fp32": "f32"}[c["precision"]], arith=c["arith"],
                         device=int(c["device"]), x0=x0, nxl=nxl, kernel=c.get("kernel", "auto"),
                         record_mask=rec_mask, record_every=int(c["record_every"]), ring_slots=ring_slots,
-                        bc_y=c.get("bc_y", "absorbing"))
+                        bc_y=c.get("bc_y", "absorbing"), record_stride=stride)
         self.engine = e
         if nranks > 1:
             # one process per GPU: fused NVLink halo push (CUDA IPC handles all-gathered over any host channel,
@@ -288,11 +304,23 @@ class Solver:
                      "fdx": fdx.reshape(-1, 1, 1), "fdy": fdy.reshape(1, -1, 1), "fdz": fdz.reshape(1, 1, -1),
                      "steps": int(self.t), "dt": float(dt), "prim_material": prim["name"], "sec_material": sec["name"],
                      "solver_cfg": json.dumps(c), "x0": int(x0), "nxl": int(nxl)}
+            if stride != (1, 1, 1):
+                # decimated volume: the file describes the decimated mesh (consumers index x / fdx by u.shape), the full
+                # mesh lines are kept beside it
+                sx_, sy_, sz_ = stride
+                xs, ys, zs = x[::sx_], y[::sy_], z[::sz_]
+                attrs.update({"x_full": x, "y_full": y, "z_full": z, "record_stride": np.array(stride, np.float64), "x": xs, "y": ys, "z": zs})
+                for key, line, shp in (("fdx", xs, (-1, 1, 1)), ("fdy", ys, (1, -1, 1)), ("fdz", zs, (1, 1, -1))):
+                    fd = np.diff(line) * si
+                    attrs[key] = fd.reshape(shp)
+                    attrs["s" + key[1:]] = (0.5 * (fd[1:] + fd[:-1])).reshape(shp)
+                P = np.ascontiguousarray(P[::sx_, ::sy_, ::sz_])
             meta = {"attrs": attrs, "density": P, "elasticity": None}
             if rec_mode == "full" and P.size <= 1 << 22:      # the reference's `elasticity` is 288 B/cell
-                meta["elasticity"] = np.array(C_out, np.float64) if dense else np.where((ids == 1)[..., None, None], sec["c"], prim["c"])
+                Cfull = np.array(C_out, np.float64) if dense else np.where((ids == 1)[..., None, None], sec["c"], prim["c"])
+                meta["elasticity"] = np.ascontiguousarray(Cfull[::stride[0], ::stride[1], ::stride[2]])
             path = self.file if nranks == 1 else "%s.rank%d" % (self.file, rank)      # one file per slab
-            self.writer = Writer(path, e, meta, frames, rec_mode, int(c["record_every"]), ring=self._full_ring, fields=fields)
+            self.writer = Writer(path, e, meta, frames, rec_mode, int(c["record_every"]), ring=self._full_ring, fields=fields, stride=stride)
             self.writer.start()
         self._rec_mode = rec_mode
         self.init_seconds = time.time() - t_init

@@ -309,3 +309,32 @@ def test_plugin_reinit_without_run_and_cancel_latency(tmp_path):
     s2.cancel()
     th.join(5)
     assert not th.is_alive() and time.time() - t0 < 1.0 and 0 < s2.stats["steps"] < 10_000_000
+
+
+@pytest.mark.parametrize("ring", [True, False])
+def test_plugin_decimated_volume_snapshots(tmp_path, ring):
+    """record = "full" with cfg["record_stride"]: every (sx, sy, sz)-th entry of the whole arrays per recorded step --
+    the way to keep volume snapshots of a grid whose full frames would not fit the recorder ring.
+    The file describes the decimated mesh (x, fdx, ... match the dataset shapes, the full mesh lines are kept as
+    x_full ...); the frames equal the reference's fields on the kept entries; ring and synchronous paths agree."""
+    from phonomena_b200.h5lite import H5Reader
+    d = H.load_golden("crystal_48x32x12")
+    st = (2, 3, 2)
+    s = make_solver(d, tmp_path, record="full", record_stride=list(st), record_every=10)
+    if not ring:
+        s.FULL_RING_MAX_FRAME_BYTES = 0
+    s.init(*fake_from_golden(d), d["steps"])
+    assert s._full_ring == ring
+    s.run()
+    r = H5Reader(s.file)
+    frames = d["steps"] // 10
+    for key in ("ux", "uy", "uz"):
+        want = d[key][::st[0], ::st[1], ::st[2]]
+        assert r.shape(key) == want.shape + (frames,), (key, r.shape(key))
+        assert np.array_equal(r.read(key, frame=frames - 1), want), key
+    assert np.array_equal(r.attrs["x"], d["x"][::2]) and np.array_equal(r.attrs["x_full"], d["x"])
+    assert r.attrs["fdx"].shape == (len(d["x"][::2]) - 1, 1, 1) and list(r.attrs["record_stride"]) == [2.0, 3.0, 2.0]
+    P = np.where(d["ids"] == 1, d["sec_p"], d["prim_p"])
+    assert np.array_equal(r.read("density"), P[::2, ::3, ::2])
+    from tests import h5check
+    h5check.validate(s.file)

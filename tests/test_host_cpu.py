@@ -111,8 +111,6 @@ def test_spectrum_matches_reference_formula(tmp_path):
     assert np.array_equal(xs, x) and np.array_equal(f, np.fft.fftfreq(N, d=dt)[:N // 2]) and np.allclose(dft, ref, rtol=1e-13, atol=0)
     _, _, d1 = analysis.spectrum(p, "uz", 0, 3, x_index=4)
     assert np.allclose(d1, np.abs(np.fft.fft(data[4, 3, 0, :] * win, norm="ortho"))[:N // 2], rtol=1e-13, atol=0)
-    out, idx = analysis.trim_trailing_zeros(d1.copy())
-    assert out.size == len(idx) <= d1.size
 
 
 def test_bench_reference_arm_contract_line():
