@@ -206,14 +206,20 @@ int phb_cancel(phb_ctx *ctx);
  * stay open until phb_writer_finish has returned.  A write error aborts the recording (phb_run then fails
  * with the errno text).  phb_writer_finish: no further frame will be produced; drain, join (at most
  * timeout_ms; 0 = 300 s), report the number of frames written and the seconds the threads spent waiting
- * for frames / writing them.  phb_destroy joins a writer that is still running. */
+ * for frames / writing them.  phb_destroy joins a writer that is still running.
+ * flags: PHB_WRITER_MMAP -- the caller has ALLOCATED every frame extent (posix_fallocate) and opened `fd` read-write:
+ * the extents are mapped MAP_SHARED and the threads copy into the page cache in parallel (pwrite on one file
+ * serialises on the inode lock); PHB_WRITER_POPULATE pre-faults the mapping.  If the mapping is refused the threads
+ * fall back to pwrite (phb_writer_mapped tells which). */
+enum { PHB_WRITER_MMAP = 1, PHB_WRITER_POPULATE = 2 };
 int phb_writer_start(phb_ctx *ctx, int32_t fd, int32_t ncomp, const int64_t *base, const int64_t *bytes,
-                     int64_t stride, int64_t frames, int32_t nthreads);
+                     int64_t stride, int64_t frames, int32_t nthreads, int32_t flags);
+int phb_writer_mapped(phb_ctx *ctx, int32_t *mapped);
 int phb_writer_finish(phb_ctx *ctx, int32_t timeout_ms, int64_t *written, double *wait_s, double *write_s);
 /* host-only exercise of the ring + writer threads (CPU tests; makes no CUDA call): a producer thread
  * pushes `frames` synthetic frames (element q of frame f = f * 1e6 + q) through a `slots`-deep ring. */
 int phb_writer_selftest(int32_t fd, int32_t ncomp, const int64_t *base, const int64_t *bytes, int64_t stride,
-                        int64_t frames, int32_t slots, int32_t nthreads, int32_t timeout_ms, int64_t *written);
+                        int64_t frames, int32_t slots, int32_t nthreads, int32_t timeout_ms, int32_t flags, int64_t *written);
 
 /* line probes and on-device spectra.
  * replaces: simulation/analysis.py:59-66 -- the reference re-reads the (x, t) matrix

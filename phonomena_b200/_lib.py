@@ -20,6 +20,7 @@ KERNEL_AUTO, KERNEL_NAIVE, KERNEL_MARCH = 0, 1, 2
 CUR, OLD = 0, 1
 REC_UX, REC_UY, REC_UZ, REC_FULL = 1, 2, 4, 8
 BC_ABSORBING, BC_PERIODIC = 0, 1
+WRITER_MMAP, WRITER_POPULATE = 1, 2
 
 # every symbol include/phb200.h declares (tests check the .so exports all of them)
 SYMBOLS = (
@@ -28,7 +29,7 @@ SYMBOLS = (
     "phb_get_material_ids", "phb_set_abc", "phb_set_source_table", "phb_set_fields", "phb_get_fields",
     "phb_get_stress", "phb_run", "phb_sync", "phb_run_timed", "phb_steps_done", "phb_launch_count",
     "phb_info", "phb_profile", "phb_comm_unique_id", "phb_comm_init", "phb_p2p_export", "phb_p2p_import", "phb_record_next", "phb_record_release",
-    "phb_record_frame_doubles", "phb_record_abort", "phb_record_timeout", "phb_cancel", "phb_writer_start", "phb_writer_finish",
+    "phb_record_frame_doubles", "phb_record_abort", "phb_record_timeout", "phb_cancel", "phb_writer_start", "phb_writer_mapped", "phb_writer_finish",
     "phb_writer_selftest", "phb_probe_add", "phb_probe_shape", "phb_probe_read", "phb_probe_dft_t", "phb_probe_dft_xt",
 )
 
@@ -101,9 +102,10 @@ def load_library(path=None):
     lib.phb_record_abort.argtypes = [vp, C.c_char_p]
     lib.phb_record_timeout.argtypes = [vp, C.c_int32]
     lib.phb_cancel.argtypes = [vp]
-    lib.phb_writer_start.argtypes = [vp, C.c_int32, C.c_int32, i64p, i64p, C.c_int64, C.c_int64, C.c_int32]
+    lib.phb_writer_start.argtypes = [vp, C.c_int32, C.c_int32, i64p, i64p, C.c_int64, C.c_int64, C.c_int32, C.c_int32]
+    lib.phb_writer_mapped.argtypes = [vp, C.POINTER(C.c_int32)]
     lib.phb_writer_finish.argtypes = [vp, C.c_int32, i64p, dp, dp]
-    lib.phb_writer_selftest.argtypes = [C.c_int32, C.c_int32, i64p, i64p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, i64p]
+    lib.phb_writer_selftest.argtypes = [C.c_int32, C.c_int32, i64p, i64p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, i64p]
     lib.phb_probe_add.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.POINTER(C.c_int32)]
     lib.phb_probe_shape.argtypes = [vp, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     lib.phb_probe_read.argtypes = [vp, C.c_int32, dp]
@@ -141,14 +143,15 @@ def device_count():
     return n.value
 
 
-def writer_selftest(fd, base, nbytes, stride, frames, slots=4, nthreads=2, timeout_ms=2000):
+def writer_selftest(fd, base, nbytes, stride, frames, slots=4, nthreads=2, timeout_ms=2000, mmap=False):
     """Host-only run of the recorder ring + native writer threads (no CUDA call); returns frames written."""
     lib = load_library()
     n = len(base)
     b = (C.c_int64 * n)(*[int(v) for v in base])
     nb = (C.c_int64 * n)(*[int(v) for v in nbytes])
     w = C.c_int64(0)
-    rc = lib.phb_writer_selftest(int(fd), n, b, nb, int(stride), int(frames), int(slots), int(nthreads), int(timeout_ms), C.byref(w))
+    rc = lib.phb_writer_selftest(int(fd), n, b, nb, int(stride), int(frames), int(slots), int(nthreads), int(timeout_ms),
+                                 WRITER_MMAP if mmap else 0, C.byref(w))
     if rc != 0:
         raise PhbError("%s (after %d frames)" % (lib.phb_last_error().decode("utf-8", "replace"), w.value))
     return w.value
@@ -423,12 +426,19 @@ class Engine:
     def record_timeout(self, timeout_ms):
         _chk(self.lib, self.lib.phb_record_timeout(self._ctx, int(timeout_ms)))
 
-    def writer_start(self, fd, base, nbytes, stride, frames, nthreads=4):
-        """Native writer threads: component c of recorded frame f goes to file offset base[c] + f * stride."""
+    def writer_start(self, fd, base, nbytes, stride, frames, nthreads=4, mmap=False, populate=False):
+        """Native writer threads: component c of recorded frame f goes to file offset base[c] + f * stride.
+        mmap: the extents are allocated and `fd` is read-write -> map them and copy in parallel (else pwrite)."""
         n = len(base)
         b = (C.c_int64 * n)(*[int(v) for v in base])
         nb = (C.c_int64 * n)(*[int(v) for v in nbytes])
-        _chk(self.lib, self.lib.phb_writer_start(self._ctx, int(fd), n, b, nb, int(stride), int(frames), int(nthreads)))
+        flags = (WRITER_MMAP if mmap else 0) | (WRITER_POPULATE if (mmap and populate) else 0)
+        _chk(self.lib, self.lib.phb_writer_start(self._ctx, int(fd), n, b, nb, int(stride), int(frames), int(nthreads), flags))
+
+    def writer_mapped(self):
+        m = C.c_int32(0)
+        _chk(self.lib, self.lib.phb_writer_mapped(self._ctx, C.byref(m)))
+        return bool(m.value)
 
     def writer_finish(self, timeout_ms=300000):
         """Drain + join; returns (frames written, seconds waiting for frames, seconds writing).  Raises on a

@@ -118,6 +118,109 @@ __global__ void k_abc_z(AbcArgs<typename A::T> p) {
 }
 
 // ---------------------------------------------------------------------------------------
+// All faces in ONE launch, for steps whose stencil kernel has applied the z = -1 face itself (StepArgs::zface):
+// what is left is the x face, the two y faces and the z face on the columns whose inputs the x / y faces change
+// (rows 0, ny-2, ny-1 and planes nx-2, nx-1).  The reference's order x -> y -> z (later faces read what earlier
+// ones wrote on shared edges) is kept WITHOUT ordering the threads: every thread evaluates the earlier faces of
+// the inner points it needs itself, from values no face writes (`nw` off the faces, `cur`), with the same mur<A>
+// -- bit-identical to the three ordered launches -- and every face entry has exactly one writer: x threads leave
+// the y-face rows and the z-face points to the later faces, y threads leave the z-face points to the z threads.
+// 1-D grid over three segments: [x: ny*nz][y: 2*(ie-ib)*nz][z: 3*(ie-ib) + 2*(ny-3)].
+// ---------------------------------------------------------------------------------------
+template <class A>
+struct FaceEval {
+    using T = typename A::T;
+    const AbcArgs<T> &p;
+    const bool has_x;
+    __device__ FaceEval(const AbcArgs<T> &p_, bool hx) : p(p_), has_x(hx) {}
+    // comp: 0 ux, 1 uy, 2 uz
+    __device__ __forceinline__ const T *cur(int c) const { return c == 0 ? p.cur.ux : c == 1 ? p.cur.uy : p.cur.uz; }
+    __device__ __forceinline__ T *nw(int c) const { return c == 0 ? p.nw.ux : c == 1 ? p.nw.uy : p.nw.uz; }
+    __device__ __forceinline__ int xplane(int c) const { return c == 0 ? p.g.nx - 2 : p.g.nx - 1; }
+    __device__ __forceinline__ T cx(int c) const { return c == 0 ? p.clx : p.ctx; }
+    // u_new after the x face
+    __device__ __forceinline__ T after_x(int c, int i, int j, int k) const {
+        const Geo<T> &g = p.g;
+        if (has_x && i == xplane(c))
+            return mur<A>(cur(c)[g.idx(i - 1, j, k)], nw(c)[g.idx(i - 1, j, k)], cur(c)[g.idx(i, j, k)], cx(c));
+        return nw(c)[g.idx(i, j, k)];
+    }
+    // y-face rows of component c: side 0 -> (face 0, inner 1), side 1 -> (last row, the one before)
+    __device__ __forceinline__ int yface(int c, int side) const { return side == 0 ? 0 : (c == 1 ? p.g.ny - 2 : p.g.ny - 1); }
+    __device__ __forceinline__ int yinner(int c, int side) const { return side == 0 ? 1 : (c == 1 ? p.g.ny - 3 : p.g.ny - 2); }
+    __device__ __forceinline__ T cy(int c, int side) const { return side == 0 ? (c == 1 ? p.cly0 : p.cty0) : (c == 1 ? p.cly1 : p.cty1); }
+    __device__ __forceinline__ T y_value(int c, int side, int i, int k) const {
+        const Geo<T> &g = p.g;
+        const int jf = yface(c, side), jn = yinner(c, side);
+        return mur<A>(cur(c)[g.idx(i, jn, k)], after_x(c, i, jn, k), cur(c)[g.idx(i, jf, k)], cy(c, side));
+    }
+    // u_new after the x and y faces
+    __device__ __forceinline__ T after_xy(int c, int i, int j, int k) const {
+        if (j == yface(c, 0)) return y_value(c, 0, i, k);
+        if (j == yface(c, 1)) return y_value(c, 1, i, k);
+        return after_x(c, i, j, k);
+    }
+    __device__ __forceinline__ bool exists(int c, int i, int j, int k) const {
+        return i < p.g.nx - (c == 0) && j < p.g.ny - (c == 1) && k < p.g.nz - (c == 2);
+    }
+    __device__ __forceinline__ int zface(int c) const { return c == 2 ? p.g.nz - 2 : p.g.nz - 1; }
+};
+
+template <class A>
+__global__ void __launch_bounds__(256) k_faces_fused(AbcArgs<typename A::T> p, int has_x) {
+    using T = typename A::T;
+    const Geo<T> &g = p.g;
+    FaceEval<A> f(p, has_x != 0);
+    const int np = p.i_end - p.i_begin;
+    const long long nX = has_x ? (long long)g.ny * g.nz : 0, nY = 2LL * np * g.nz;
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < nX) {                                   // ---- x face: thread (j, k), k fastest
+        const int k = (int)(t % g.nz), j = (int)(t / g.nz);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const int i = f.xplane(c);
+            if (!f.exists(c, i, j, k) || k == f.zface(c) || j == f.yface(c, 0) || j == f.yface(c, 1)) continue;
+            f.nw(c)[g.idx(i, j, k)] = f.after_x(c, i, j, k);
+        }
+        return;
+    }
+    t -= nX;
+    if (t < nY) {                                   // ---- y faces: thread (side, i, k), k fastest
+        const int k = (int)(t % g.nz);
+        const int q = (int)(t / g.nz), i = p.i_begin + q % np, side = q / np;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const int jf = f.yface(c, side);
+            if (!f.exists(c, i, jf, k) || k == f.zface(c)) continue;
+            f.nw(c)[g.idx(i, jf, k)] = f.y_value(c, side, i, k);
+        }
+        return;
+    }
+    t -= nY;
+    {                                               // ---- z face on the columns the x / y faces touched
+        int i, j;
+        if (t < 3LL * np) {
+            i = p.i_begin + (int)(t % np);
+            const int r = (int)(t / np);
+            j = r == 0 ? 0 : g.ny - 3 + r;          // rows 0, ny-2, ny-1
+        } else {
+            t -= 3LL * np;
+            if (!has_x || t >= 2LL * (g.ny - 3)) return;
+            i = g.nx - 2 + (int)(t / (g.ny - 3));
+            j = 1 + (int)(t % (g.ny - 3));          // rows 1 .. ny-3 (the others are in the first set)
+            if (i < p.i_begin || i >= p.i_end) return;
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const int kf = f.zface(c), kn = kf - 1;
+            if (!f.exists(c, i, j, kf)) continue;
+            const T cz = c == 2 ? p.clz : p.ctz;
+            f.nw(c)[g.idx(i, j, kf)] = mur<A>(f.cur(c)[g.idx(i, j, kn)], f.after_xy(c, i, j, kn), f.cur(c)[g.idx(i, j, kf)], cz);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // Fused halo push: after the stencil kernel has stored the edge planes into the neighbours' ghost
 // planes, tell them which step is complete (flags live in the NEIGHBOUR's memory, CUDA IPC).
 // ---------------------------------------------------------------------------------------

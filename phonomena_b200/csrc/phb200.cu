@@ -124,6 +124,7 @@ struct phb_ctx {
     cudaStream_t zst = nullptr;        // second launch stream of a split step (the z-tile that owns the z = -1 face)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int zsplit = 1;                    // PHB_ZSPLIT=0: one launch for all z-tiles
+    int faces_fused = 1;               // PHB_FACES_FUSED=0: ordered x, y, z face launches even when the z face is fused into the stencil
     cudaEvent_t ev_edge = nullptr, ev_comm = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
     void *buf[3][3] = {};      // [buffer][component], each (nxl+2) planes
     int cur = 0;               // buffer holding u; old = (cur+2)%3, new = (cur+1)%3
@@ -619,6 +620,24 @@ struct Engine : IEngine {
         CU(cudaGetLastError());
         return 0;
     }
+    // x face (if this rank owns it) + y faces + z face of planes [ib, ie): one launch when the stencil kernel has applied the
+    // z face itself (k_faces_fused), else the ordered launches x, y, z
+    int faces(int ib, int ie, bool with_x) {
+        if (ie <= ib) return 0;
+        if (c->faces_fused && use_march() && zface_fused() && !periodic_y() && !comp() && !getenv("PHB_DEBUG_ZF_NOP") && c->cfg.ny >= 5) {
+            AbcArgs<T> a = abc_args(ib, ie);
+            const long long n = (with_x ? (long long)c->cfg.ny * c->cfg.nz : 0) + 2LL * (ie - ib) * c->cfg.nz + 3LL * (ie - ib) +
+                                (with_x ? 2LL * (c->cfg.ny - 3) : 0);
+            const unsigned gr = (unsigned)((n + 255) / 256);
+            if (c->cfg.arith == PHB_EXACT) k_faces_fused<Ar<T, true>><<<gr, 256, 0, c->st>>>(a, with_x ? 1 : 0);
+            else k_faces_fused<Ar<T, false>><<<gr, 256, 0, c->st>>>(a, with_x ? 1 : 0);
+            c->launches++;
+            CU(cudaGetLastError());
+            return 0;
+        }
+        if (with_x) OK(abc_x());
+        return abc_yz(ib, ie);
+    }
     bool periodic_y() const { return c->cfg.bc_y == PHB_BC_PERIODIC; }
     // periodic y boundaries: recompute the rows the wrapped stresses reach + the displacement copies (k_pbc_y); must run
     // right after the stencil launch of the same planes, BEFORE the x face (the reference order: pbc, then apply_u_abc)
@@ -748,8 +767,7 @@ struct Engine : IEngine {
             k_signal<<<1, 1, 0, c->st>>>(hasL ? c->peer_flags[0] + 1 : nullptr, hasR ? c->peer_flags[1] + 0 : nullptr, c->flags + 8);
             k_wait_flags<<<1, 1, 0, c->st>>>(hasL ? c->flags + 0 : nullptr, hasR ? c->flags + 1 : nullptr, c->flags + 8);
             c->launches += 2;
-            if (last) OK(abc_x());
-            OK(abc_yz(x0 - (hasL ? 1 : 0), xe + (hasR ? 1 : 0)));
+            OK(faces(x0 - (hasL ? 1 : 0), xe + (hasR ? 1 : 0), last));
             return 0;
         }
         static const int fake_edges = getenv("PHB_DEBUG_FAKE_EDGES") ? atoi(getenv("PHB_DEBUG_FAKE_EDGES")) : 0;   // timing aid
@@ -774,14 +792,12 @@ struct Engine : IEngine {
             CU(cudaEventRecord(c->ev_comm, c->cst));
             OK(physics(ib, ie));
             OK(pbc_y(ib, ie));
-            if (last) OK(abc_x());
-            OK(abc_yz(ib, ie));
+            OK(faces(ib, ie, last));
             CU(cudaStreamWaitEvent(c->st, c->ev_comm, 0));
         } else {
             OK(physics(x0, xe));
             OK(pbc_y(x0, xe));
-            if (last) OK(abc_x());
-            OK(abc_yz(x0, xe));
+            OK(faces(x0, xe, last));
         }
         return 0;
     }
@@ -963,6 +979,7 @@ int phb_create(const phb_cfg *cfg, phb_ctx **out) {
     cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
     if (const char *e = getenv("PHB_ZSPLIT")) c->zsplit = atoi(e) != 0;
+    if (const char *e = getenv("PHB_FACES_FUSED")) c->faces_fused = atoi(e) != 0;
     cudaEventCreateWithFlags(&c->ev_edge, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->ev_comm, cudaEventDisableTiming);
     cudaEventCreate(&c->ev_t0);
@@ -1494,12 +1511,18 @@ static int writer_setup(NativeWriter &w, RecRing &r, int fd, int32_t ncomp, cons
     return 0;
 }
 int phb_writer_start(phb_ctx *c, int32_t fd, int32_t ncomp, const int64_t *base, const int64_t *bytes, int64_t stride,
-                     int64_t frames, int32_t nthreads) {
+                     int64_t frames, int32_t nthreads, int32_t flags) {
     if (!c || !c->rec.host) return fail("recording not enabled");
     if (c->wr.started) return fail("writer already started");
     if (c->rec.produced.load() != 0) return fail("frames were recorded before the writer started");
     OK(writer_setup(c->wr, c->rec, fd, ncomp, base, bytes, stride, frames));
+    if (flags & PHB_WRITER_MMAP) c->wr.map_extents((flags & PHB_WRITER_POPULATE) != 0);     // falls back to pwrite when the mapping is refused
     return c->wr.start(&c->rec, nthreads > 0 ? nthreads : 4);
+}
+int phb_writer_mapped(phb_ctx *c, int32_t *mapped) {
+    if (!c || !mapped) return fail("null argument");
+    *mapped = c->wr.map != nullptr;
+    return 0;
 }
 int phb_writer_finish(phb_ctx *c, int32_t timeout_ms, int64_t *written, double *wait_s, double *write_s) {
     if (!c) return fail("null context");
@@ -1515,7 +1538,7 @@ int phb_writer_finish(phb_ctx *c, int32_t timeout_ms, int64_t *written, double *
 // doubles, frame f element q = f * 1e6 + q, through a `slots`-deep ring; the writer threads store them at
 // base[c] + f * stride.  abort_at >= 0: the producer stops there as if cancelled.  No CUDA call is made.
 int phb_writer_selftest(int32_t fd, int32_t ncomp, const int64_t *base, const int64_t *bytes, int64_t stride, int64_t frames,
-                        int32_t slots, int32_t nthreads, int32_t timeout_ms, int64_t *written) {
+                        int32_t slots, int32_t nthreads, int32_t timeout_ms, int32_t flags, int64_t *written) {
     if (slots < 1 || frames < 0) return fail("bad arguments");
     RecRing r;
     long long fb = 0;
@@ -1529,6 +1552,7 @@ int phb_writer_selftest(int32_t fd, int32_t ncomp, const int64_t *base, const in
     r.slot_tt.assign(slots, -1);
     NativeWriter w;
     OK(writer_setup(w, r, fd, ncomp, base, bytes, stride, frames));
+    if ((flags & PHB_WRITER_MMAP) && !w.map_extents((flags & PHB_WRITER_POPULATE) != 0)) return fail("mmap of the frame extents failed: %s", strerror(errno));
     w.start(&r, nthreads > 0 ? nthreads : 2);
     int rc = 0;
     for (long long f = 0; f < frames && !rc; ++f) {

@@ -92,7 +92,7 @@ class H5Writer:
 
     def __init__(self, path):
         # raw descriptor + positional writes: frames of different datasets can be written by several threads at once
-        self.fd = os.open(path, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o644)
+        self.fd = os.open(path, os.O_RDWR | os.O_CREAT | os.O_TRUNC, 0o644)      # read-write: the native writer may map the frame extents
         self._end = 96                      # superblock placeholder
         self._lock = threading.Lock()
         self.attrs = {}
@@ -135,8 +135,9 @@ class H5Writer:
         copies.  Best effort."""
         try:
             os.posix_fallocate(self.fd, self._end if start is None else int(start), int(nbytes))
+            return True
         except (OSError, AttributeError):
-            pass
+            return False
 
     def create_chunked(self, name, shape):
         d = _Chunked(name, shape)

@@ -87,7 +87,7 @@ class Writer:
     join(300), base_solver.py:89-92,148,274)."""
 
     WRITE_THREADS = 4      # native threads, each writes whole frames
-    PREALLOCATE_MAX_BYTES = 2 << 30
+    PREALLOCATE_MAX_BYTES = 8 << 30
 
     def __init__(self, path, engine, meta, frames, mode, record_every, ring=True, fields=("ux", "uy", "uz"), stride=(1, 1, 1)):
         self.path, self.e, self.mode, self.frames = path, engine, mode, frames
@@ -112,13 +112,14 @@ class Writer:
         # The static datasets (density alone is Nx*Ny*Nz doubles) are pushed out now, in init(), like the reference's
         # Writer.init (base_solver.py:105-133): otherwise the kernel's dirty-page writeback of them throttles the
         # frame appends of the stepping loop.
-        self._layout = None
+        self._layout, self._mapped = None, False
         if self.ring and frames > 0:
             start = self.h5._end
             base, stride = self.h5.reserve_frames(list(self.ds.values()), frames)
             self._layout = (base, [d.frame_bytes for d in self.ds.values()], stride)
-            if stride * frames <= self.PREALLOCATE_MAX_BYTES:
-                self.h5.preallocate(stride * frames, start)
+            # allocated extents can be mapped: the native threads then copy into the page cache without sharing the
+            # file's inode lock (pwrite serialises on it); unallocated ones are written with pwrite (ENOSPC -> error, not SIGBUS)
+            self._mapped = stride * frames <= self.PREALLOCATE_MAX_BYTES and bool(self.h5.preallocate(self.h5._end - start, start))
         self.h5.settle()
         self.written = 0
         self.wait_seconds = self.write_seconds = 0.0     # writer threads: waiting for frames / writing them
@@ -129,7 +130,10 @@ class Writer:
         if self._layout is None:
             return
         base, nbytes, stride = self._layout
-        self.e.writer_start(self.h5.fd, base, nbytes, stride, self.frames, self.WRITE_THREADS)
+        # populate: the allocated pages are entered into the mapping now (no zeroing, ~0.2 us per page), so the stepping
+        # loop's copies take no page faults (first-touch faults on one file serialise on its page-cache lock: 6.8 GB/s
+        # for any number of threads, measured)
+        self.e.writer_start(self.h5.fd, base, nbytes, stride, self.frames, self.WRITE_THREADS, mmap=self._mapped, populate=self._mapped)
         self.started = True
 
     # full mode without a ring: called synchronously by the run loop

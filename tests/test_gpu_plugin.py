@@ -238,14 +238,17 @@ def test_plugin_record_fields_subset(tmp_path):
 
 
 # ---- the recorder cannot hang run() (reference: queue.get(timeout=120), join(300), base_solver.py:89-92,148,274) ----
-def test_plugin_writer_failure_raises_instead_of_hanging(tmp_path):
+def test_plugin_writer_failure_raises_instead_of_hanging(tmp_path, monkeypatch):
     """The writer threads hit a write error on the first frame (their descriptor is swapped for a read-only one):
     Solver.run() must raise with the errno text within about a second, not wait for a free ring slot forever."""
     import os
     from phonomena_b200 import _lib
+    from phonomena_b200.solver_b200 import Writer
     d = H.load_golden("crystal_48x32x12")
     s = make_solver(d, tmp_path, record="surface", chunk_steps=20)
+    monkeypatch.setattr(Writer, "PREALLOCATE_MAX_BYTES", 0)      # unallocated extents -> the threads pwrite() (allocated ones are mapped)
     s.init(*fake_from_golden(d), 400)            # 400 frames >> 32 ring slots
+    assert not s.engine.writer_mapped()
     ro = os.open(os.devnull, os.O_RDONLY)
     keep = os.dup(s.writer.h5.fd)
     os.dup2(ro, s.writer.h5.fd)                  # native pwrite -> EBADF
@@ -294,6 +297,7 @@ def test_plugin_reinit_without_run_and_cancel_latency(tmp_path):
     s = make_solver(d, tmp_path, record="surface")
     s.file = str(tmp_path / "first.h5")
     s.init(*fake_from_golden(d), 30)
+    assert s.engine.writer_mapped()              # allocated extents: the native threads copy through a shared mapping
     first = s.file
     s.file = str(tmp_path / "second.h5")
     s.init(*fake_from_golden(d), 30)

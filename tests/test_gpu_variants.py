@@ -20,6 +20,7 @@ VARIANTS = [
     {"PHB_MARCH_RW": "2", "PHB_ZFUSE": "1", "PHB_MARCH_CHUNKS": "3"},
     {"PHB_MARCH_RW": "2", "PHB_ZFUSE": "1", "PHB_ZSPLIT": "0"},      # fused face, one launch for all z-tiles (default: split step)
     {"PHB_MARCH_RW": "2", "PHB_ZFUSE": "1", "PHB_GRAPH": "0"},
+    {"PHB_MARCH_RW": "2", "PHB_ZFUSE": "1", "PHB_FACES_FUSED": "0"},   # ordered x, y, z face launches instead of the one-launch faces kernel
 ]
 SHAPES = [
     ((24, 33, 128), 9),      # fp64: 2 z-tiles, face in the last lane of the second; 3 y-tiles

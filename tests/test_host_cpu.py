@@ -221,8 +221,9 @@ class _FakeRingEngine:
     def planes(self, comp):
         return self.nx - 1 if comp == 0 else self.nx
 
-    def writer_start(self, fd, base, nbytes, stride, frames, nthreads=4):
+    def writer_start(self, fd, base, nbytes, stride, frames, nthreads=4, mmap=False, populate=False):
         self.args = (fd, list(base), list(nbytes), stride, frames, nthreads)
+        self.mmap = mmap
 
     def writer_finish(self, timeout_ms=300000):
         from phonomena_b200 import _lib
@@ -231,7 +232,8 @@ class _FakeRingEngine:
         if self.fail_fd:
             fd = os.open(os.devnull, os.O_RDONLY)       # pwrite on a read-only descriptor: EBADF
         try:
-            n = _lib.writer_selftest(fd, base, nbytes, stride, self.produce, slots=3, nthreads=nthreads, timeout_ms=2000)
+            n = _lib.writer_selftest(fd, base, nbytes, stride, self.produce, slots=3, nthreads=nthreads, timeout_ms=2000,
+                                     mmap=self.mmap and not self.fail_fd)
         except _lib.PhbError:
             self.writer_stats = (0, 0.0, 0.0)
             raise
@@ -308,13 +310,15 @@ def test_native_ring_flow_control_and_threads(tmp_path):
     """phb_writer_selftest directly: more frames than ring slots (the producer has to wait for in-order releases), 1..4
     writer threads, interleaved component extents."""
     from phonomena_b200 import _lib
-    for nthreads in (1, 2, 4):
+    for nthreads, mm in ((1, False), (2, False), (4, False), (3, True)):
         p = str(tmp_path / ("ring%d.bin" % nthreads))
         fd = os.open(p, os.O_RDWR | os.O_CREAT | os.O_TRUNC, 0o644)
         nb = [24 * 8, 40 * 8]
         stride, frames = sum(nb) + 64, 50
-        base = [128, 128 + nb[0]]
-        assert _lib.writer_selftest(fd, base, nb, stride, frames, slots=3, nthreads=nthreads) == frames
+        base = [5000, 5000 + nb[0]]          # not page-aligned: the mapped path maps from the page below
+        if mm:
+            os.posix_fallocate(fd, 0, base[0] + stride * frames)
+        assert _lib.writer_selftest(fd, base, nb, stride, frames, slots=3, nthreads=nthreads, mmap=mm) == frames
         os.close(fd)
         raw = np.fromfile(p, dtype="<f8")
         for f in (0, 1, 17, 49):
