@@ -358,10 +358,13 @@ def run_b200(args):
         "config": {"workload": workload_name(n, args.scaling),
                    "arith": arith, "material": "indexed (1-byte stencil class)", "kernel": info["kernel"],
                    "l2": "inputs (%.1f GB/GPU) far exceed the 126 MB L2; no explicit flush" % (info["device_bytes"] / 1e9),
-                   "launch_path": "CUDA-graph replay of the step" if n == 1 else "stream launches",
+                   "launch_path": "CUDA-graph replay of the step" if (n == 1 or halo in ("p2p", "fused")) else "stream launches",
                    "halo": {"none": "none", "nccl": "NCCL send/recv of 3 planes per direction per step, overlapped with the interior update",
-                            "p2p": "fused: the stencil kernel stores its edge planes into the neighbours' ghost planes over NVLink (CUDA IPC), "
-                                   "stream-ordered flag write/wait, no collective call"}[halo]},
+                            "p2p": "peer memory: after the faces of a step one kernel stores the two finished edge planes into the neighbours' ghost "
+                                   "planes over NVLink (CUDA IPC) and publishes the step number; a 1-thread kernel waits for the neighbours'; no collective call; "
+                                   "the whole slab step is replayed as a CUDA graph",
+                            "fused": "the stencil kernel stores its edge planes into the neighbours' ghost planes over NVLink (CUDA IPC) while it computes them, "
+                                     "flag write/wait kernels, no collective call"}[halo]},
         "clocks": clocks, "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None,
                      "traffic": traffic, "peak_source": peak_src, "kernel": "k_step_march", "kernel_ms_per_step": kms / K if K else None, "kernel_launches_per_step": kn / K if K else None,

@@ -170,8 +170,14 @@ int phb_comm_init(phb_ctx *ctx, const char id[128], int32_t rank, int32_t nranks
  * hands each rank the exports of its left and right neighbours (NULL at the ends).  The stencil kernel then
  * stores the slab's first / last plane straight into the neighbours' ghost planes; a stream-ordered flag
  * write / wait replaces the collective; each rank applies the y / z absorbing faces to its ghost planes.
- * replaces: nothing in the reference. */
+ * replaces: nothing in the reference.
+ * Two ways to move the planes (phb_p2p_mode; default 0): 0 = after the faces of a step one small kernel copies the two
+ * finished edge planes into the neighbours' ghost planes (16-byte peer stores) and publishes the step number in their
+ * flag words; 1 = "fused": the stencil kernel itself stores the edge planes while it computes them, the receiver
+ * applies the y / z faces to its ghost planes.  Both are bit-identical to a single-GPU run; mode 0 is faster here
+ * (the transfer is 7 us of NVLink time per step, the in-kernel stores cost the memory-bound stencil 38 us). */
 int phb_p2p_export(phb_ctx *ctx, char handles[256], int32_t *nxl);
+int phb_p2p_mode(phb_ctx *ctx, int32_t fused_in_kernel);
 int phb_p2p_import(phb_ctx *ctx, int32_t rank, int32_t nranks, const char *left, int32_t left_nxl,
                    const char *right, int32_t right_nxl);
 

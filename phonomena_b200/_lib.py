@@ -28,7 +28,7 @@ SYMBOLS = (
     "phb_set_spacing", "phb_set_material_table", "phb_set_material_dense", "phb_set_material_ids", "phb_gen_material_ids",
     "phb_get_material_ids", "phb_set_abc", "phb_set_source_table", "phb_set_fields", "phb_get_fields",
     "phb_get_stress", "phb_run", "phb_sync", "phb_run_timed", "phb_steps_done", "phb_launch_count",
-    "phb_info", "phb_profile", "phb_comm_unique_id", "phb_comm_init", "phb_p2p_export", "phb_p2p_import", "phb_record_next", "phb_record_release",
+    "phb_info", "phb_profile", "phb_comm_unique_id", "phb_comm_init", "phb_p2p_export", "phb_p2p_import", "phb_p2p_mode", "phb_record_next", "phb_record_release",
     "phb_record_frame_doubles", "phb_record_abort", "phb_record_timeout", "phb_cancel", "phb_writer_start", "phb_writer_mapped", "phb_writer_finish",
     "phb_writer_selftest", "phb_probe_add", "phb_probe_shape", "phb_probe_read", "phb_probe_dft_t", "phb_probe_dft_xt",
 )
@@ -95,6 +95,7 @@ def load_library(path=None):
     lib.phb_comm_init.argtypes = [vp, C.c_char_p, C.c_int32, C.c_int32]
     lib.phb_p2p_export.argtypes = [vp, C.c_char_p, C.POINTER(C.c_int32)]
     lib.phb_p2p_import.argtypes = [vp, C.c_int32, C.c_int32, C.c_char_p, C.c_int32, C.c_char_p, C.c_int32]
+    lib.phb_p2p_mode.argtypes = [vp, C.c_int32]
     lib.phb_record_next.argtypes = [vp, C.POINTER(dp), C.POINTER(C.c_int64), C.c_int32]
     lib.phb_record_release.argtypes = [vp]
     lib.phb_record_frame_doubles.argtypes = [vp, C.POINTER(C.c_int64)]
@@ -354,13 +355,14 @@ class Engine:
         _chk(self.lib, self.lib.phb_p2p_import(self._ctx, int(rank), int(nranks), left[0], int(left[1]), right[0], int(right[1])))
 
     def connect(self, rank, nranks, allgather, broadcast, mode=None):
-        """Set up the halo exchange of an x-slab context.  mode 'p2p' (default: fused NVLink peer stores,
-        CUDA IPC) or 'nccl'; `allgather(obj) -> list` and `broadcast(obj) -> obj` are host channels."""
+        """Set up the halo exchange of an x-slab context.  mode 'p2p' (default: a push kernel stores the finished edge
+        planes into the neighbours' ghost planes over NVLink, CUDA IPC), 'fused' (the stencil kernel stores them itself)
+        or 'nccl'; `allgather(obj) -> list` and `broadcast(obj) -> obj` are host channels."""
         import os
         mode = mode or os.environ.get("PHB_HALO", "p2p")
         if nranks == 1:
             return "none"
-        if mode == "p2p":
+        if mode in ("p2p", "fused"):
             # every rank runs the same two collectives whatever fails locally (a rank that skipped one would pair
             # its next all-gather with the others' previous one)
             try:
@@ -375,7 +377,8 @@ class Engine:
                 except PhbError:
                     ok = 0
             if all(allgather(ok)):
-                return "p2p"
+                _chk(self.lib, self.lib.phb_p2p_mode(self._ctx, 1 if mode == "fused" else 0))
+                return mode
         self.comm_init(broadcast(comm_unique_id() if rank == 0 else None), rank, nranks)
         return "nccl"
 

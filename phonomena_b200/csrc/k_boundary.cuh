@@ -224,6 +224,48 @@ __global__ void __launch_bounds__(256) k_faces_fused(AbcArgs<typename A::T> p, i
 // Fused halo push: after the stencil kernel has stored the edge planes into the neighbours' ghost
 // planes, tell them which step is complete (flags live in the NEIGHBOUR's memory, CUDA IPC).
 // ---------------------------------------------------------------------------------------
+// Halo push after the step (default peer-memory mode): copy the slab's first / last owned plane of u_new (all faces
+// applied: the values are final) into the matching ghost plane of the left / right neighbour -- 16-byte vectors over
+// NVLink through the CUDA-IPC mapping -- then the last block to finish publishes the step number in the neighbours'
+// flag words.  src / dst: [edge 0 = low, 1 = high][component]; a null dst row = no neighbour on that side.
+// 12 MB per step at 512^2 fp64: ~7 us of NVLink time; storing the same planes from inside the stencil kernel
+// (template PUSH of k_step_march, kept as halo mode "fused") costs that memory-bound kernel 38 us through its
+// instruction footprint alone (measured with device-local targets).
+struct PushArgs {
+    const void *src[2][3];
+    void *dst[2][3];
+    long long vecs;              // 16-byte vectors per plane
+    volatile int *flag[2];       // the neighbours' flag words (theirs to read): [0] left neighbour's "from right", [1] right neighbour's "from left"
+    const int *steps_done;
+    unsigned *arrive;            // block-arrival counter (zero between launches)
+};
+__global__ void __launch_bounds__(256) k_push_signal(PushArgs a) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        if (!a.dst[e][0]) continue;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const int4 *s = static_cast<const int4 *>(a.src[e][c]);
+            int4 *d = static_cast<int4 *>(a.dst[e][c]);
+            for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < a.vecs; v += stride) d[v] = s[v];
+        }
+    }
+    __threadfence_system();          // this thread's peer stores are visible system-wide
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned ticket = atomicAdd(a.arrive, 1u);
+        if (ticket == gridDim.x - 1) {       // every block's stores are fenced: publish
+            *a.arrive = 0;
+            const int step = *a.steps_done + 1;
+            __threadfence_system();
+            if (a.flag[0]) *a.flag[0] = step;
+            if (a.flag[1]) *a.flag[1] = step;
+            __threadfence_system();
+        }
+    }
+}
+
 // The step number is not a launch argument: both kernels read the count of completed steps from device memory and the
 // wait kernel advances it, so the whole slab step can be replayed as a CUDA graph (phb200.cu step()).
 __global__ void k_signal(volatile int *left_flag, volatile int *right_flag, const int *steps_done) {

@@ -139,6 +139,7 @@ struct phb_ctx {
     void *tab = nullptr;       // class table, ncls x CLS_W
     int ncls = 0;
     void *line_save = nullptr;
+    void *dbg_push = nullptr;  // PHB_DEBUG_SELF_PUSH scratch planes
     double *w = nullptr;       // source samples for steps w_base .. w_base + nw - 1 (capacity w_cap, pointer kept while it fits)
     long long nw = 0, w_base = 0, w_cap = 0;
     long long *src_idx = nullptr;   // device: index into w of the next step's sample (k_source advances it)
@@ -157,6 +158,7 @@ struct phb_ctx {
     ncclComm_t comm = nullptr;
     int rank = 0, nranks = 1;
     // fused halo push over NVLink peer memory (CUDA IPC); halo = 0 none, 1 NCCL, 2 peer stores
+    int push_fused = 0;          // halo == 2: 0 = push kernel after the faces (default), 1 = edge planes stored by the stencil kernel itself
     int halo = 0;
     void *peer_buf[2][3] = {};   // [left | right][buffer]: the neighbour's displacement buffers, mapped
     int peer_nxl[2] = {0, 0};
@@ -450,7 +452,7 @@ struct Engine : IEngine {
         StepArgs<T> p;
         p.edge_b = edge_b;
         for (int q = 0; q < 3; ++q) p.push_lo[q] = p.push_hi[q] = nullptr;
-        if (c->halo == 2 && use_march()) {
+        if (c->halo == 2 && c->push_fused && use_march()) {
             const int bn = b_new();
             if (c->peer_buf[0][bn]) {       // left neighbour: its right ghost plane (local plane nxl_L + 1)
                 const long long comp = (long long)(c->peer_nxl[0] + 2) * c->ps;
@@ -459,6 +461,17 @@ struct Engine : IEngine {
             if (c->peer_buf[1][bn]) {       // right neighbour: its left ghost plane (local plane 0)
                 const long long comp = (long long)(c->peer_nxl[1] + 2) * c->ps;
                 for (int q = 0; q < 3; ++q) p.push_hi[q] = (T *)c->peer_buf[1][bn] + q * comp;
+            }
+        }
+        {   // timing aid (single GPU): run the PUSH instantiation with device-local scratch planes as "neighbours" --
+            // separates what the push code costs the kernel from what NVLink and the system fence cost
+            static const int self_push = getenv("PHB_DEBUG_SELF_PUSH") ? atoi(getenv("PHB_DEBUG_SELF_PUSH")) : 0;
+            if (self_push && c->nranks == 1 && use_march()) {
+                if (!c->dbg_push) OK(dmalloc(c, &c->dbg_push, (size_t)6 * c->ps * c->esz));
+                for (int q = 0; q < 3; ++q) {
+                    if (self_push & 1) p.push_lo[q] = (T *)c->dbg_push + (long long)q * c->ps;
+                    if (self_push & 2) p.push_hi[q] = (T *)c->dbg_push + (long long)(3 + q) * c->ps;
+                }
             }
         }
         p.g = geo();
@@ -519,7 +532,7 @@ struct Engine : IEngine {
                 else if (c->mR == 8 && c->mNST == 4) r = launch_march_cfg<A, 8, 4>(p, m, mp, ch, c->st);
                 if (r == -2) return fail("no marching-kernel instantiation for R=%d NST=%d", c->mR, c->mNST);
                 if (r == -3) return fail("internal: fused z face requested for a marching-kernel configuration without it");
-                if (r < 0 && (c->cfg.kernel == PHB_KERNEL_MARCH || c->halo == 2))
+                if (r < 0 && (c->cfg.kernel == PHB_KERNEL_MARCH || (c->halo == 2 && c->push_fused)))
                     return fail("marching kernel needs more shared memory than the device allows (%d classes)", c->ncls);
                 if (r >= 0) { c->launches += r; return 0; }
                 c->maps_ok = false;      // kernel = auto: too many stencil classes for the shared-memory table -> naive kernel
@@ -553,7 +566,7 @@ struct Engine : IEngine {
         // cells has too few tiles to fill the SMs -- one thread per cell is faster there (measured: 32^3 25 vs 33 us per
         // step, equal at 64^3, 2x slower at 96^3; EXACT arithmetic 8x faster on the 31x21x6 default.json grid)
         // (not for slabs that push their halos from inside the marching kernel)
-        if (c->cfg.kernel == PHB_KERNEL_AUTO && c->halo != 2 && (long long)c->cfg.nxl * c->cfg.ny * c->cfg.nz < 200000) return false;
+        if (c->cfg.kernel == PHB_KERNEL_AUTO && !(c->halo == 2 && c->push_fused) && (long long)c->cfg.nxl * c->cfg.ny * c->cfg.nz < 200000) return false;
         return c->maps_ok && march_fits();
     }
     // x-chunks per launch: fill whole waves of (148 SMs x resident blocks) with the (y,z) tiles
@@ -760,9 +773,35 @@ struct Engine : IEngine {
             // then a stream-ordered flag write / wait (no NCCL kernel, no SM taken from the stencil), and the y / z
             // absorbing faces are applied to the owned planes AND to the received ghost planes (same formula and
             // inputs as on the owning rank, so the result stays bit-identical).
-            if (!use_march()) return fail("halo=p2p needs the marching kernel");
-            if (periodic_y()) return fail("periodic y boundaries need the NCCL halo path (the fix-up rows are final only after the stencil kernel)");
             const bool hasL = c->rank > 0, hasR = c->rank < c->nranks - 1;
+            if (!c->push_fused) {
+                // stencil (one launch, or the split pair) -> periodic fix-up -> all faces of the owned planes -> push the two
+                // finished edge planes into the neighbours' ghost planes + signal -> wait for the neighbours' signal
+                OK(physics(x0, xe));
+                OK(pbc_y(x0, xe));
+                OK(faces(x0, xe, last));
+                PushArgs a{};
+                const int bn = b_new();
+                for (int q = 0; q < 3; ++q) {
+                    const char *mine = (const char *)c->buf[bn][q];
+                    a.src[0][q] = mine + (size_t)1 * c->ps * c->esz;                      // first owned plane (local plane 1)
+                    a.src[1][q] = mine + (size_t)c->cfg.nxl * c->ps * c->esz;             // last owned plane
+                    if (hasL) a.dst[0][q] = (char *)c->peer_buf[0][bn] + ((size_t)q * (c->peer_nxl[0] + 2) + (c->peer_nxl[0] + 1)) * c->ps * c->esz;
+                    if (hasR) a.dst[1][q] = (char *)c->peer_buf[1][bn] + ((size_t)q * (c->peer_nxl[1] + 2)) * c->ps * c->esz;
+                }
+                a.vecs = (long long)c->ps * (long long)c->esz / 16;
+                a.flag[0] = hasL ? c->peer_flags[0] + 1 : nullptr;
+                a.flag[1] = hasR ? c->peer_flags[1] + 0 : nullptr;
+                a.steps_done = c->flags + 8;
+                a.arrive = (unsigned *)(c->flags + 9);
+                k_push_signal<<<96, 256, 0, c->st>>>(a);
+                k_wait_flags<<<1, 1, 0, c->st>>>(hasL ? c->flags + 0 : nullptr, hasR ? c->flags + 1 : nullptr, c->flags + 8);
+                c->launches += 2;
+                CU(cudaGetLastError());
+                return 0;
+            }
+            if (!use_march()) return fail("halo=fused needs the marching kernel");
+            if (periodic_y()) return fail("periodic y boundaries: use halo mode p2p or nccl (the fix-up rows are final only after the stencil kernel)");
             OK(physics(x0, xe));
             k_signal<<<1, 1, 0, c->st>>>(hasL ? c->peer_flags[0] + 1 : nullptr, hasR ? c->peer_flags[1] + 0 : nullptr, c->flags + 8);
             k_wait_flags<<<1, 1, 0, c->st>>>(hasL ? c->flags + 0 : nullptr, hasR ? c->flags + 1 : nullptr, c->flags + 8);
@@ -1053,7 +1092,7 @@ int phb_destroy(phb_ctx *c) {
     cudaFree(c->flags);
     for (int b = 0; b < 3; ++b) cudaFree(c->buf[b][0]);
     for (int a = 0; a < 6; ++a) cudaFree(c->sp[a]);
-    cudaFree(c->tab); cudaFree(c->ids); cudaFree(c->code); cudaFree(c->line_save);
+    cudaFree(c->tab); cudaFree(c->ids); cudaFree(c->code); cudaFree(c->line_save); cudaFree(c->dbg_push);
     graph_invalidate(c);
     if (c->w) cudaFree(c->w);
     cudaFree(c->src_idx);
@@ -1420,7 +1459,7 @@ int phb_p2p_import(phb_ctx *c, int32_t rank, int32_t nranks, const char *left, i
     graph_invalidate(c);
     if (nranks < 1 || rank < 0 || rank >= nranks) return fail("bad rank %d of %d", rank, nranks);
     if (!c->flags) return fail("call phb_p2p_export first");
-    if (c->cfg.bc_y == PHB_BC_PERIODIC) return fail("periodic y boundaries: use the NCCL halo path (phb_comm_init)");
+
     c->rank = rank; c->nranks = nranks;
     if (nranks == 1) return 0;
     if (c->cfg.nxl < 4) return fail("a slab needs at least 4 planes (got %d)", c->cfg.nxl);
@@ -1443,6 +1482,14 @@ int phb_p2p_import(phb_ctx *c, int32_t rank, int32_t nranks, const char *left, i
         CU(cudaStreamSynchronize(c->st));
     }
     c->halo = 2;
+    return 0;
+}
+
+int phb_p2p_mode(phb_ctx *c, int32_t fused_in_kernel) {
+    ENTER(c);
+    graph_invalidate(c);
+    if (fused_in_kernel && c->cfg.bc_y == PHB_BC_PERIODIC) return fail("periodic y boundaries cannot use the in-kernel halo push");
+    c->push_fused = fused_in_kernel ? 1 : 0;
     return 0;
 }
 

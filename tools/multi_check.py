@@ -74,10 +74,11 @@ def main():
     from phonomena_b200 import selfcheck
     ok = True
     # (1) what bench.py runs before every N > 1 timed region: random initial fields, the production halo path
-    res = selfcheck.slabs_vs_single(rank, world, local, allgather, broadcast, halo=halo)
-    if rank == 0:
-        print(json.dumps({"check": "selfcheck.slabs_vs_single", "world": world, **res}), flush=True)
-    ok = ok and res["slabs_bit_identical"]
+    for hm_ in dict.fromkeys([halo, "fused", "nccl"]):      # the production mode first, then the in-kernel push and the NCCL fallback
+        res = selfcheck.slabs_vs_single(rank, world, local, allgather, broadcast, halo=hm_)
+        if rank == 0:
+            print(json.dumps({"check": "selfcheck.slabs_vs_single", "world": world, **res}), flush=True)
+        ok = ok and res["slabs_bit_identical"] and res["halo"] == hm_
     # (2) source-driven runs from zero fields, marching kernel over the chosen halo mode and the per-cell kernel over NCCL
     for dtype, arith, kernel in (("f64", "fast", "march"), ("f64", "exact", "march"), ("f32", "fast", "march"), ("f64", "fast", "naive")):
         case = crystal_case(nx, ny, nz)
