@@ -236,7 +236,7 @@ struct PushArgs {
     void *dst[2][3];
     long long vecs;              // 16-byte vectors per plane
     volatile int *flag[2];       // the neighbours' flag words (theirs to read): [0] left neighbour's "from right", [1] right neighbour's "from left"
-    const int *steps_done;
+    int *steps_done;             // device count of completed steps: this kernel publishes steps_done + 1 and advances it
     unsigned *arrive;            // block-arrival counter (zero between launches)
 };
 __global__ void __launch_bounds__(256) k_push_signal(PushArgs a) {
@@ -248,6 +248,7 @@ __global__ void __launch_bounds__(256) k_push_signal(PushArgs a) {
         for (int c = 0; c < 3; ++c) {
             const int4 *s = static_cast<const int4 *>(a.src[e][c]);
             int4 *d = static_cast<int4 *>(a.dst[e][c]);
+#pragma unroll 4
             for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < a.vecs; v += stride) d[v] = s[v];
         }
     }
@@ -262,6 +263,7 @@ __global__ void __launch_bounds__(256) k_push_signal(PushArgs a) {
             if (a.flag[0]) *a.flag[0] = step;
             if (a.flag[1]) *a.flag[1] = step;
             __threadfence_system();
+            *a.steps_done = step;
         }
     }
 }
@@ -275,14 +277,30 @@ __global__ void k_signal(volatile int *left_flag, volatile int *right_flag, cons
     if (right_flag) *right_flag = step;
     __threadfence_system();
 }
-// Wait until both neighbours have signalled this step (their edge planes sit in my ghost planes), then count the step.
-// One thread; it runs after the stencil launch of the step has completed (stream order), so it takes no SM from it.
-__global__ void k_wait_flags(const volatile int *from_left, const volatile int *from_right, int *steps_done) {
-    const int step = *steps_done + 1;
-    if (from_left) while (*from_left < step) __nanosleep(40);
-    if (from_right) while (*from_right < step) __nanosleep(40);
+// Wait until both neighbours' flags have reached steps_done + plus, then (inc) count the step.  One thread.
+//  * push-after-faces mode: plus = 0, inc = 0, at the START of a step -- "the edge planes of every step I have completed
+//    have arrived in my ghost planes"; it gates only the launches that read ghost planes (phb200.cu launch_step).
+//  * in-kernel push mode: plus = 1, inc = 1, at the end of the step.
+// timeout_ns > 0 (phb_sync only): give up after that long -- a neighbour that is gone must not hang the caller.
+__global__ void k_wait_flags(const volatile int *from_left, const volatile int *from_right, int *steps_done, int plus, int inc,
+                             unsigned long long timeout_ns) {
+    const int step = *steps_done + plus;
+    unsigned long long t0 = 0;
+    if (timeout_ns) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (int side = 0; side < 2; ++side) {
+        const volatile int *f = side ? from_right : from_left;
+        if (!f) continue;
+        while (*f < step) {
+            __nanosleep(40);
+            if (timeout_ns) {
+                unsigned long long t;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                if (t - t0 > timeout_ns) return;
+            }
+        }
+    }
     __threadfence_system();
-    *steps_done = step;
+    if (inc) *steps_done = step;
 }
 
 // ---------------------------------------------------------------------------------------

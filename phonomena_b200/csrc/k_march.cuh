@@ -258,9 +258,9 @@ k_step_march(const __grid_constant__ MarchMaps tm, StepArgs<typename A::T> p, Ma
     const int r0 = w * RW;                           // first tile row of this warp (rows r0 .. r0 + RW - 1)
     const int k0t = (blockIdx.x + p.ztile0) * TZ;    // first cell of the tile row
     const int j0 = blockIdx.y * C_::TY;              // first output row
-    // planes [ia, ib): x-chunk blockIdx.z of [i_begin, i_end), or (edge launch) the single planes i_begin / edge_b
+    // planes [ia, ib): x-chunk blockIdx.z of [i_begin, i_end), or (edge launch) the two chunks that start at i_begin / edge_b
     const int ia = (p.edge_b >= 0) ? (blockIdx.z == 0 ? p.i_begin : p.edge_b) : p.i_begin + blockIdx.z * chunk;
-    const int ib = (p.edge_b >= 0) ? ia + 1 : min(ia + chunk, p.i_end);
+    const int ib = (p.edge_b >= 0) ? ia + chunk : min(ia + chunk, p.i_end);
     if (ia >= ib) return;
     const int j = j0 - 1 + r0;                       // y index of the warp's first row
     const int kb = k0t + lane * V;                   // first cell of this lane

@@ -16,7 +16,7 @@ struct StepArgs {
     // fused halo push (k_march only): where the first / last owned plane of u_new also goes -- the matching ghost
     // plane of the left / right neighbour's buffer, mapped through CUDA IPC (NVLink peer stores); null = none
     T *push_lo[3], *push_hi[3];
-    int edge_b;           // >= 0: second single plane of an 'edge launch' (planes i_begin and edge_b, one chunk each)
+    int edge_b;           // >= 0: 'edge launch' of two chunks of (i_end - i_begin) planes, starting at i_begin and at edge_b
     // fused z = -1 absorbing face (k_march only, not in COMP mode): the block that owns k = nz-1 applies the Mur
     // formula to its own results before storing them (the face points and their inner neighbours sit in one
     // lane); the host then re-applies the face only where the x / y faces change its inputs (k_abc_z, edges only)

@@ -123,6 +123,13 @@ struct phb_ctx {
     cudaStream_t st = nullptr, cst = nullptr;
     cudaStream_t zst = nullptr;        // second launch stream of a split step (the z-tile that owns the z = -1 face)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // slab mode, push-after-faces: the x-chunks that read ghost planes run on their own lane, gated by the neighbours'
+    // flags, beside the chunks that do not (launch_step)
+    cudaStream_t est = nullptr, ezst = nullptr;
+    cudaEvent_t ev_efork = nullptr, ev_ejoin = nullptr, ev_lane = nullptr, ev_lane_done = nullptr;
+    int overlap = 0;                   // PHB_OVERLAP=1: edge x-chunks on their own lane behind the flag wait, middle chunks ungated
+                                       // (measured at 2 GPUs, 512 planes each: 1.706 vs 1.693 ms -- the two extra x-chunks cost more
+                                       // than the hidden wait saves; kept as an opt-in, tested bit-identical)
     int zsplit = 1;                    // PHB_ZSPLIT=0: one launch for all z-tiles
     int faces_fused = 1;               // PHB_FACES_FUSED=0: ordered x, y, z face launches even when the z face is fused into the stencil
     cudaEvent_t ev_edge = nullptr, ev_comm = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
@@ -447,8 +454,11 @@ struct Engine : IEngine {
 
     // ---- one time step -----------------------------------------------------------------------
     // edge_b >= 0: edge launch of the two single planes ib and edge_b (marching kernel only)
-    int physics(int ib, int ie, int edge_b = -1) {
+    int physics(int ib, int ie, int edge_b = -1, int lane = 0) {
         if (ie <= ib) return 0;
+        // launch lane: 0 = the step's main stream, 1 = the edge lane of a slab step
+        cudaStream_t S = lane ? c->est : c->st, ZS = lane ? c->ezst : c->zst;
+        cudaEvent_t EF = lane ? c->ev_efork : c->ev_fork, EJ = lane ? c->ev_ejoin : c->ev_join;
         StepArgs<T> p;
         p.edge_b = edge_b;
         for (int q = 0; q < 3; ++q) p.push_lo[q] = p.push_hi[q] = nullptr;
@@ -496,7 +506,7 @@ struct Engine : IEngine {
                 }
             }
             pe = &c->prof_ev[c->prof_used++];
-            CU(cudaEventRecord(pe->first, c->st));
+            CU(cudaEventRecord(pe->first, S));
         }
         if (c->cfg.kernel == PHB_KERNEL_MARCH && !march)
             return fail("kernel=march requested but the marching kernel does not support this grid");
@@ -504,32 +514,32 @@ struct Engine : IEngine {
         auto run = [&]<class A>() -> int {
             if (march) {
                 const MarchMaps &mp = c->mm[b_cur()];
-                const int ch = plan_chunks(ie - ib);
+                const int ch = edge_b >= 0 ? 1 : plan_chunks(ie - ib);      // an edge launch is two chunks of ie - ib planes
                 int r = -2;
-                // Split step: the z = -1 face code costs the stencil kernel more through its instruction footprint (the
-                // plane loop no longer fits the 32 KB instruction cache level, every block pays) than through the work
-                // itself (only the blocks of the last z-tile run it).  So the tile that owns the face is launched on its
+                // Split step: the instantiation with the z = -1 face code is slower for EVERY block (+22 us per step even
+                // when the face code never runs: the extra path costs the plane loop scheduling freedom), while the work
+                // itself concerns only the blocks of the last z-tile.  So the tile that owns the face is launched on its
                 // own with the face instantiation, on a second (higher-priority) stream beside the launch for all other
                 // z-tiles without it; both finish inside the same waves of blocks.
                 const int V = VecOf<T>::V, nzt = (c->nzp + 32 * V - 1) / (32 * V);
-                if (p.zface == 1 && c->zsplit && nzt >= 2 && edge_b < 0 && c->mR == 16 && c->mNST == 4 && c->mRW == 2) {
-                    CU(cudaEventRecord(c->ev_fork, c->st));
-                    CU(cudaStreamWaitEvent(c->zst, c->ev_fork, 0));
+                if (p.zface == 1 && c->zsplit && nzt >= 2 && (edge_b < 0 || ie - ib >= 16) && c->mR == 16 && c->mNST == 4 && c->mRW == 2) {
+                    CU(cudaEventRecord(EF, S));
+                    CU(cudaStreamWaitEvent(ZS, EF, 0));
                     StepArgs<T> pz = p;
                     pz.ztile0 = nzt - 1;
-                    const int rz = launch_march_cfg<A, 16, 4, 2>(pz, m, mp, ch, c->zst, 1);
-                    CU(cudaEventRecord(c->ev_join, c->zst));
+                    const int rz = launch_march_cfg<A, 16, 4, 2>(pz, m, mp, ch, ZS, 1);
+                    CU(cudaEventRecord(EJ, ZS));
                     p.zface = 0;
-                    r = launch_march_cfg<A, 16, 4, 2>(p, m, mp, ch, c->st, nzt - 1);
-                    CU(cudaStreamWaitEvent(c->st, c->ev_join, 0));
+                    r = launch_march_cfg<A, 16, 4, 2>(p, m, mp, ch, S, nzt - 1);
+                    CU(cudaStreamWaitEvent(S, EJ, 0));
                     if (rz < 0 || r < 0) return fail("marching kernel needs more shared memory than the device allows (%d classes)", c->ncls);
                     c->launches += rz + r;
                     return 0;
                 }
-                if (c->mR == 16 && c->mNST == 4 && c->mRW == 2) r = launch_march_cfg<A, 16, 4, 2>(p, m, mp, ch, c->st);
-                else if (c->mR == 16 && c->mNST == 4) r = launch_march_cfg<A, 16, 4>(p, m, mp, ch, c->st);
-                else if (c->mR == 16 && c->mNST == 3) r = launch_march_cfg<A, 16, 3>(p, m, mp, ch, c->st);
-                else if (c->mR == 8 && c->mNST == 4) r = launch_march_cfg<A, 8, 4>(p, m, mp, ch, c->st);
+                if (c->mR == 16 && c->mNST == 4 && c->mRW == 2) r = launch_march_cfg<A, 16, 4, 2>(p, m, mp, ch, S);
+                else if (c->mR == 16 && c->mNST == 4) r = launch_march_cfg<A, 16, 4>(p, m, mp, ch, S);
+                else if (c->mR == 16 && c->mNST == 3) r = launch_march_cfg<A, 16, 3>(p, m, mp, ch, S);
+                else if (c->mR == 8 && c->mNST == 4) r = launch_march_cfg<A, 8, 4>(p, m, mp, ch, S);
                 if (r == -2) return fail("no marching-kernel instantiation for R=%d NST=%d", c->mR, c->mNST);
                 if (r == -3) return fail("internal: fused z face requested for a marching-kernel configuration without it");
                 if (r < 0 && (c->cfg.kernel == PHB_KERNEL_MARCH || (c->halo == 2 && c->push_fused)))
@@ -539,13 +549,14 @@ struct Engine : IEngine {
             }
             {
                 dim3 bl = block_for(c->cfg.nz), gr = grid3(c->cfg.nz, c->cfg.ny, ie - ib, bl);
-                k_step_naive<A, MatCls<T>><<<gr, bl, 0, c->st>>>(p, m);
+                if (edge_b >= 0) return fail("internal: edge launch without the marching kernel");
+                k_step_naive<A, MatCls<T>><<<gr, bl, 0, S>>>(p, m);
                 c->launches++;
             }
             return 0;
         };
         OK(dispatch(run));
-        if (pe) CU(cudaEventRecord(pe->second, c->st));
+        if (pe) CU(cudaEventRecord(pe->second, S));
         CU(cudaGetLastError());
         return 0;
     }
@@ -777,7 +788,27 @@ struct Engine : IEngine {
             if (!c->push_fused) {
                 // stencil (one launch, or the split pair) -> periodic fix-up -> all faces of the owned planes -> push the two
                 // finished edge planes into the neighbours' ghost planes + signal -> wait for the neighbours' signal
-                OK(physics(x0, xe));
+                int *const fl = hasL ? c->flags + 0 : nullptr, *const fr = hasR ? c->flags + 1 : nullptr;
+                const int nxl = xe - x0, cl = (nxl + 3) / 4;
+                if (c->overlap && use_march() && nxl >= 384) {
+                    // The first and the last quarter of the slab read a ghost plane: they run on the edge lane, behind the wait
+                    // for the neighbours' flags of the previous step; the middle half does not and starts at once, so the
+                    // neighbours' push, the flag round trip and the skew between the ranks hide behind half a step of work.
+                    cudaStream_t L = c->prof ? c->st : c->est;       // (profiling pass: one lane, so the per-launch times add up)
+                    if (!c->prof) {
+                        CU(cudaEventRecord(c->ev_lane, c->st));
+                        CU(cudaStreamWaitEvent(c->est, c->ev_lane, 0));
+                    }
+                    k_wait_flags<<<1, 1, 0, L>>>(fl, fr, c->flags + 8, 0, 0, 0ULL);
+                    OK(physics(x0, x0 + cl, xe - cl, c->prof ? 0 : 1));
+                    if (!c->prof) CU(cudaEventRecord(c->ev_lane_done, c->est));
+                    OK(physics(x0 + cl, xe - cl));
+                    if (!c->prof) CU(cudaStreamWaitEvent(c->st, c->ev_lane_done, 0));
+                } else {
+                    k_wait_flags<<<1, 1, 0, c->st>>>(fl, fr, c->flags + 8, 0, 0, 0ULL);
+                    OK(physics(x0, xe));
+                }
+                c->launches++;
                 OK(pbc_y(x0, xe));
                 OK(faces(x0, xe, last));
                 PushArgs a{};
@@ -794,9 +825,8 @@ struct Engine : IEngine {
                 a.flag[1] = hasR ? c->peer_flags[1] + 0 : nullptr;
                 a.steps_done = c->flags + 8;
                 a.arrive = (unsigned *)(c->flags + 9);
-                k_push_signal<<<96, 256, 0, c->st>>>(a);
-                k_wait_flags<<<1, 1, 0, c->st>>>(hasL ? c->flags + 0 : nullptr, hasR ? c->flags + 1 : nullptr, c->flags + 8);
-                c->launches += 2;
+                k_push_signal<<<444, 256, 0, c->st>>>(a);      // 3 blocks per SM: ~5 vectors per thread and plane, loads in flight together
+                c->launches++;
                 CU(cudaGetLastError());
                 return 0;
             }
@@ -804,7 +834,7 @@ struct Engine : IEngine {
             if (periodic_y()) return fail("periodic y boundaries: use halo mode p2p or nccl (the fix-up rows are final only after the stencil kernel)");
             OK(physics(x0, xe));
             k_signal<<<1, 1, 0, c->st>>>(hasL ? c->peer_flags[0] + 1 : nullptr, hasR ? c->peer_flags[1] + 0 : nullptr, c->flags + 8);
-            k_wait_flags<<<1, 1, 0, c->st>>>(hasL ? c->flags + 0 : nullptr, hasR ? c->flags + 1 : nullptr, c->flags + 8);
+            k_wait_flags<<<1, 1, 0, c->st>>>(hasL ? c->flags + 0 : nullptr, hasR ? c->flags + 1 : nullptr, c->flags + 8, 1, 1, 0ULL);
             c->launches += 2;
             OK(faces(x0 - (hasL ? 1 : 0), xe + (hasR ? 1 : 0), last));
             return 0;
@@ -1017,6 +1047,15 @@ int phb_create(const phb_cfg *cfg, phb_ctx **out) {
     }
     cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
+    {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (cudaStreamCreateWithFlags(&c->est, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaStreamCreateWithPriority(&c->ezst, cudaStreamNonBlocking, hi) != cudaSuccess) return cleanup(fail("stream create failed"));
+    }
+    for (cudaEvent_t *ev : {&c->ev_efork, &c->ev_ejoin, &c->ev_lane, &c->ev_lane_done}) cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
+    if (const char *e = getenv("PHB_OVERLAP")) c->overlap = atoi(e) != 0;
+    c->zsplit = cfg->dtype == PHB_F64;      // fp32 has 4 z-tiles: the face tile is a quarter of the grid and the split is indifferent to worse (0.848 vs 0.844 ms)
     if (const char *e = getenv("PHB_ZSPLIT")) c->zsplit = atoi(e) != 0;
     if (const char *e = getenv("PHB_FACES_FUSED")) c->faces_fused = atoi(e) != 0;
     cudaEventCreateWithFlags(&c->ev_edge, cudaEventDisableTiming);
@@ -1104,6 +1143,8 @@ int phb_destroy(phb_ctx *c) {
     for (auto &pr : c->probes) cudaFree(pr.trace);
     for (auto &pe : c->prof_ev) { cudaEventDestroy(pe.first); cudaEventDestroy(pe.second); }
     if (c->zst) { cudaStreamSynchronize(c->zst); cudaStreamDestroy(c->zst); }
+    for (cudaStream_t q : {c->est, c->ezst}) if (q) { cudaStreamSynchronize(q); cudaStreamDestroy(q); }
+    for (cudaEvent_t ev : {c->ev_efork, c->ev_ejoin, c->ev_lane, c->ev_lane_done}) if (ev) cudaEventDestroy(ev);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->ev_edge) cudaEventDestroy(c->ev_edge);
@@ -1350,6 +1391,12 @@ int phb_run(phb_ctx *c, int64_t nsteps) {
 }
 int phb_sync(phb_ctx *c) {
     ENTER(c);
+    if (c->halo == 2 && !c->push_fused && c->nranks > 1 && c->flags) {
+        // the neighbours' pushes of every completed step have landed in my ghost planes (so that a neighbour that is a
+        // little behind never stores into memory I have released); bounded: a neighbour that is gone must not hang us
+        k_wait_flags<<<1, 1, 0, c->st>>>(c->rank > 0 ? c->flags + 0 : nullptr, c->rank < c->nranks - 1 ? c->flags + 1 : nullptr,
+                                         c->flags + 8, 0, 0, 10000000000ULL);
+    }
     CU(cudaStreamSynchronize(c->st));
     CU(cudaStreamSynchronize(c->cst));
     if (c->rst) CU(cudaStreamSynchronize(c->rst));
