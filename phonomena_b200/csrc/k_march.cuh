@@ -236,7 +236,11 @@ struct MarchMaps {
 };
 
 // ---- the kernel ---------------------------------------------------------------------------------
-template <class A, int R, int NST, bool PUSH, int RW, bool ZF = false>
+// K0 = false: the launch covers no block with k = 0 (StepArgs::ztile0 >= 1), so the first-element spacing selects of the
+// free-surface plane (App. B #1-#3) -- 9 % of the fp64 instruction mix, needed by one thread of one z-tile -- fold away.
+// EDGE: the launch covers only the first (1) or only the last (2) z-tile, which has no left / right halo column: the
+// single-lane sections that rebuild the halo stresses there (5-6 % of a plane's issue slots) fold away; 0 = any tiles.
+template <class A, int R, int NST, bool PUSH, int RW, bool ZF = false, bool K0 = true, int EDGE = 0>
 __global__ void __launch_bounds__(R / RW * 32, ((R <= 8 && RW == 1) ? 2 : 1))
 k_step_march(const __grid_constant__ MarchMaps tm, StepArgs<typename A::T> p, MatCls<typename A::T> m, int chunk) {
     using T = typename A::T;
@@ -264,7 +268,7 @@ k_step_march(const __grid_constant__ MarchMaps tm, StepArgs<typename A::T> p, Ma
     if (ia >= ib) return;
     const int j = j0 - 1 + r0;                       // y index of the warp's first row
     const int kb = k0t + lane * V;                   // first cell of this lane
-    const bool k0c = (kb == 0);                      // element 0 of this thread is the k = 0 plane
+    const bool k0c = K0 && (kb == 0);                // element 0 of this thread is the k = 0 plane
     const int nplanes = (ib - ia) + 2;               // planes ia-1 .. ib, consumed in order q = 0, 1, ...
     const int lbase = (ia - 1) - g.x0 + 1;           // local plane index of q = 0
 
@@ -357,8 +361,8 @@ k_step_march(const __grid_constant__ MarchMaps tm, StepArgs<typename A::T> p, Ma
         need_normal[q] = (rr != 0);
         any_out = any_out || row_out[q];
     }
-    const bool haveL = (lane == 0) && (k0t >= 1);                  // halo column kL = k0t-1 exists
-    const bool haveR = (lane == 31) && (k0t + TZ <= g.nz - 1);     // halo column kR = k0t+TZ exists
+    const bool haveL = (EDGE != 1) && (lane == 0) && (k0t >= 1);                  // halo column kL = k0t-1 exists
+    const bool haveR = (EDGE != 2) && (lane == 31) && (k0t + TZ <= g.nz - 1);     // halo column kR = k0t+TZ exists
     const int eo = r0 * ROWE + (lane + 1) * V;         // own vector (row 0 of the warp) inside a u_cur component tile (elements)
     const int eS = (r0 >= 1) ? -ROWE : 0;              // row below the warp's first row (clamped)
     const int eN = (r0 + RW - 1 <= R - 2) ? ROWE : 0;  // row above the warp's last row (clamped), relative to that row
@@ -820,19 +824,29 @@ inline bool make_class_map(CUtensorMap *tm, void *base, int nzp, int ny, int pla
 template <class T> inline const char *march_name() { return "march_tma"; }
 
 // returns launches made (1), 0 for an empty range, -1 if the shared-memory request is refused
+// part: 0 = any z-tiles (with the k = 0 selects); split steps: 1 = z-tile 0 alone, 2 = the last z-tile alone, 3 = tiles in
+// between (ztile0 >= 1, not the last) -- each picks the instantiation without what it cannot need
 template <class A, int R, int NST, int RW = 1, bool PUSH = false>
 inline int launch_march_cfg(const StepArgs<typename A::T> &p, const MatCls<typename A::T> &m, const MarchMaps &maps,
-                            int chunks, cudaStream_t st, int ntiles = 0) {
+                            int chunks, cudaStream_t st, int ntiles = 0, int part = 0) {
     using T = typename A::T;
     using C_ = MarchCfg<T, R, NST, RW>;
     if constexpr (!PUSH) {
-        if (p.push_lo[0] || p.push_hi[0]) return launch_march_cfg<A, R, NST, RW, true>(p, m, maps, chunks, st, ntiles);
+        if (p.push_lo[0] || p.push_hi[0]) return launch_march_cfg<A, R, NST, RW, true>(p, m, maps, chunks, st, ntiles, 0);
     }
     constexpr bool kHasZF = (RW == 2) && !A::COMP;     // instantiations with the fused z face (StepArgs::zface)
+    constexpr bool kParts = (RW == 2) && !PUSH && !A::COMP;      // the specialised instantiations of a split step exist
     if (p.zface && !kHasZF) return -3;
-    auto kern = (kHasZF && p.zface) ? k_step_march<A, R, NST, PUSH, RW, kHasZF> : k_step_march<A, R, NST, PUSH, RW, false>;
-    static size_t attr_by_dev2[2][64] = {};   // per template instantiation and device (the attribute is per device)
-    size_t (&attr_by_dev)[64] = attr_by_dev2[p.zface ? 1 : 0];
+    if (!kParts) part = 0;
+    if ((part == 1 && (p.ztile0 != 0 || ntiles != 1 || p.zface)) || (part == 2 && ntiles != 1) || (part == 3 && (p.ztile0 < 1 || p.zface))) return -3;
+    constexpr int E1 = kParts ? 1 : 0, E2 = kParts ? 2 : 0;
+    auto kern = k_step_march<A, R, NST, PUSH, RW, false, true, 0>;
+    if (part == 1) kern = k_step_march<A, R, NST, PUSH, RW, false, true, E1>;
+    else if (part == 3) kern = k_step_march<A, R, NST, PUSH, RW, false, !kParts, 0>;
+    else if (part == 2) kern = p.zface ? k_step_march<A, R, NST, PUSH, RW, kHasZF, !kParts, E2> : k_step_march<A, R, NST, PUSH, RW, false, !kParts, E2>;
+    else if (p.zface) kern = k_step_march<A, R, NST, PUSH, RW, kHasZF, true, 0>;
+    static size_t attr_by_dev2[8][64] = {};   // per template instantiation and device (the attribute is per device)
+    size_t (&attr_by_dev)[64] = attr_by_dev2[(p.zface ? 1 : 0) + 2 * part];
     int dev = 0;
     cudaGetDevice(&dev);
     size_t &attr_bytes = attr_by_dev[dev & 63];

@@ -122,6 +122,8 @@ struct phb_ctx {
     int device = 0;
     cudaStream_t st = nullptr, cst = nullptr;
     cudaStream_t zst = nullptr;        // second launch stream of a split step (the z-tile that owns the z = -1 face)
+    cudaStream_t kst = nullptr;        // third: the z-tile that owns k = 0
+    cudaEvent_t ev_kjoin = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // slab mode, push-after-faces: the x-chunks that read ghost planes run on their own lane, gated by the neighbours'
     // flags, beside the chunks that do not (launch_step)
@@ -523,17 +525,30 @@ struct Engine : IEngine {
                 // z-tiles without it; both finish inside the same waves of blocks.
                 const int V = VecOf<T>::V, nzt = (c->nzp + 32 * V - 1) / (32 * V);
                 if (p.zface == 1 && c->zsplit && nzt >= 2 && (edge_b < 0 || ie - ib >= 16) && c->mR == 16 && c->mNST == 4 && c->mRW == 2) {
+                    // parts: [face tile: ZF instantiation] [tile 0: with the k = 0 selects] [tiles between: neither] -- the
+                    // middle part is the bulk and stays on the lane's main stream; PHB_ZSPLIT=2: face tile + the rest (round 2a)
+                    const bool three = c->zsplit == 1 && nzt >= 3 && lane == 0;
                     CU(cudaEventRecord(EF, S));
                     CU(cudaStreamWaitEvent(ZS, EF, 0));
                     StepArgs<T> pz = p;
                     pz.ztile0 = nzt - 1;
-                    const int rz = launch_march_cfg<A, 16, 4, 2>(pz, m, mp, ch, ZS, 1);
+                    const int rz = launch_march_cfg<A, 16, 4, 2>(pz, m, mp, ch, ZS, 1, 2);
                     CU(cudaEventRecord(EJ, ZS));
                     p.zface = 0;
-                    r = launch_march_cfg<A, 16, 4, 2>(p, m, mp, ch, S, nzt - 1);
+                    int r0 = 0;
+                    if (three) {
+                        CU(cudaStreamWaitEvent(c->kst, EF, 0));
+                        r0 = launch_march_cfg<A, 16, 4, 2>(p, m, mp, ch, c->kst, 1, 1);       // z-tile 0
+                        CU(cudaEventRecord(c->ev_kjoin, c->kst));
+                        p.ztile0 = 1;
+                        r = launch_march_cfg<A, 16, 4, 2>(p, m, mp, ch, S, nzt - 2, 3);       // z-tiles 1 .. nzt-2
+                        CU(cudaStreamWaitEvent(S, c->ev_kjoin, 0));
+                    } else {
+                        r = launch_march_cfg<A, 16, 4, 2>(p, m, mp, ch, S, nzt - 1, nzt == 2 ? 1 : 0);
+                    }
                     CU(cudaStreamWaitEvent(S, EJ, 0));
-                    if (rz < 0 || r < 0) return fail("marching kernel needs more shared memory than the device allows (%d classes)", c->ncls);
-                    c->launches += rz + r;
+                    if (rz < 0 || r < 0 || r0 < 0) return fail("marching kernel needs more shared memory than the device allows (%d classes)", c->ncls);
+                    c->launches += rz + r + r0;
                     return 0;
                 }
                 if (c->mR == 16 && c->mNST == 4 && c->mRW == 2) r = launch_march_cfg<A, 16, 4, 2>(p, m, mp, ch, S);
@@ -1044,6 +1059,8 @@ int phb_create(const phb_cfg *cfg, phb_ctx **out) {
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
         if (cudaStreamCreateWithPriority(&c->zst, cudaStreamNonBlocking, hi) != cudaSuccess) return cleanup(fail("stream create failed"));
+        if (cudaStreamCreateWithPriority(&c->kst, cudaStreamNonBlocking, hi) != cudaSuccess) return cleanup(fail("stream create failed"));
+        cudaEventCreateWithFlags(&c->ev_kjoin, cudaEventDisableTiming);
     }
     cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
@@ -1056,7 +1073,7 @@ int phb_create(const phb_cfg *cfg, phb_ctx **out) {
     for (cudaEvent_t *ev : {&c->ev_efork, &c->ev_ejoin, &c->ev_lane, &c->ev_lane_done}) cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
     if (const char *e = getenv("PHB_OVERLAP")) c->overlap = atoi(e) != 0;
     c->zsplit = cfg->dtype == PHB_F64;      // fp32 has 4 z-tiles: the face tile is a quarter of the grid and the split is indifferent to worse (0.848 vs 0.844 ms)
-    if (const char *e = getenv("PHB_ZSPLIT")) c->zsplit = atoi(e) != 0;
+    if (const char *e = getenv("PHB_ZSPLIT")) c->zsplit = atoi(e);
     if (const char *e = getenv("PHB_FACES_FUSED")) c->faces_fused = atoi(e) != 0;
     cudaEventCreateWithFlags(&c->ev_edge, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->ev_comm, cudaEventDisableTiming);
@@ -1143,6 +1160,8 @@ int phb_destroy(phb_ctx *c) {
     for (auto &pr : c->probes) cudaFree(pr.trace);
     for (auto &pe : c->prof_ev) { cudaEventDestroy(pe.first); cudaEventDestroy(pe.second); }
     if (c->zst) { cudaStreamSynchronize(c->zst); cudaStreamDestroy(c->zst); }
+    if (c->kst) { cudaStreamSynchronize(c->kst); cudaStreamDestroy(c->kst); }
+    if (c->ev_kjoin) cudaEventDestroy(c->ev_kjoin);
     for (cudaStream_t q : {c->est, c->ezst}) if (q) { cudaStreamSynchronize(q); cudaStreamDestroy(q); }
     for (cudaEvent_t ev : {c->ev_efork, c->ev_ejoin, c->ev_lane, c->ev_lane_done}) if (ev) cudaEventDestroy(ev);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);

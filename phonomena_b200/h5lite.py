@@ -471,7 +471,7 @@ def merge_slabs(paths, out_path):
         if int(r.attrs["x0"]) != x0:
             raise ValueError("slab files do not tile x: expected a slab starting at %d, found %d" % (x0, int(r.attrs["x0"])))
         x0 += int(r.attrs["nxl"])
-    nx = len(np.atleast_1d(rs[0].attrs["x"]))
+    nx = len(np.atleast_1d(rs[0].attrs.get("x_full", rs[0].attrs["x"])))      # decimated volumes keep the full mesh lines as x_full
     if x0 != nx:
         raise ValueError("slab files cover %d of %d planes" % (x0, nx))
     names = [k for k in ("ux", "uy", "uz") if all(k in r.datasets for r in rs)]       # cfg["record_fields"] may drop some

@@ -1,6 +1,6 @@
 """Every configuration of the marching kernel gives the reference's bits: one / two rows per warp
 (PHB_MARCH_RW), the z = -1 absorbing face inside the stencil kernel or as its own kernel (PHB_ZFUSE), the
-step split into a launch for the face-owning z-tile beside one for the others or not (PHB_ZSPLIT),
+step split into specialised launches per z-tile class or not (PHB_ZSPLIT),
 several z-tiles, y-tiles and x-chunks, grids whose nz makes the fused face possible (nz a multiple of
 the vector width) and grids where the host must fall back to the separate face kernel.  fp64 EXACT
 arithmetic is compared bit for bit with the C oracle (which follows base_solver.py:245-260, 323-571);
@@ -18,7 +18,9 @@ VARIANTS = [
     {"PHB_MARCH_RW": "2", "PHB_ZFUSE": "0"},
     {"PHB_MARCH_RW": "1"},
     {"PHB_MARCH_RW": "2", "PHB_ZFUSE": "1", "PHB_MARCH_CHUNKS": "3"},
-    {"PHB_MARCH_RW": "2", "PHB_ZFUSE": "1", "PHB_ZSPLIT": "0"},      # fused face, one launch for all z-tiles (default: split step)
+    {"PHB_MARCH_RW": "2", "PHB_ZFUSE": "1", "PHB_ZSPLIT": "0"},      # fused face, one launch for all z-tiles
+    {"PHB_MARCH_RW": "2", "PHB_ZFUSE": "1", "PHB_ZSPLIT": "1"},      # split step, three parts: k = 0 tile | tiles between | face tile (fp64 default)
+    {"PHB_MARCH_RW": "2", "PHB_ZFUSE": "1", "PHB_ZSPLIT": "2"},      # split step, two parts: face tile | the rest
     {"PHB_MARCH_RW": "2", "PHB_ZFUSE": "1", "PHB_GRAPH": "0"},
     {"PHB_MARCH_RW": "2", "PHB_ZFUSE": "1", "PHB_FACES_FUSED": "0"},   # ordered x, y, z face launches instead of the one-launch faces kernel
 ]
