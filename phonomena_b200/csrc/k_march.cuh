@@ -45,6 +45,8 @@
 #pragma once
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include <type_traits>
 
 #include "k_naive.cuh"
@@ -784,9 +786,20 @@ inline PFN_encodeTiled get_encode_tiled() {
     return fn;
 }
 
+// L2 promotion of the TMA loads (PHB_TMA_PROMO = 0 | 64 | 128 | 256).  Default 64 B: the step is split into launches per
+// z-tile class, and where the neighbour tile runs at another time a tile's 16-byte z-halo vector costs a DRAM fetch of
+// the promotion size -- 512^3 split step, 256 -> 64 B: fp64 1.627 -> 1.607 ms, fp32 0.883 -> 0.829 ms (one launch for all
+// tiles is indifferent to it: 0.842 ms at any size).
+inline CUtensorMapL2promotion tma_promotion(int esz) {
+    static const int env = getenv("PHB_TMA_PROMO") ? atoi(getenv("PHB_TMA_PROMO")) : -1;
+    const int v = env >= 0 ? env : 64;
+    (void)esz;
+    return v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+         : v == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+}
 // 3-D tensor map over a (planes, ny, nzp) box of `esz`-byte elements with box (bx, by, 1).
 inline bool make_map3(CUtensorMap *tm, CUtensorMapDataType dt, int esz, void *base, int nzp, int ny, int planes, int bx,
-                      int by) {
+                      int by, int field_esz) {
     PFN_encodeTiled enc = get_encode_tiled();
     if (!enc) return false;
     const cuuint64_t dims[3] = {(cuuint64_t)nzp, (cuuint64_t)ny, (cuuint64_t)planes};
@@ -794,7 +807,7 @@ inline bool make_map3(CUtensorMap *tm, CUtensorMapDataType dt, int esz, void *ba
     const cuuint32_t box[3] = {(cuuint32_t)bx, (cuuint32_t)by, 1u};
     const cuuint32_t estr[3] = {1u, 1u, 1u};
     return enc(tm, dt, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+               tma_promotion(field_esz), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 // 4-D tensor map over the three components of one displacement buffer (allocated back to back):
 // dims (nzp, ny, planes, 3), box (bx, by, 1, 3).
@@ -807,7 +820,7 @@ inline bool make_map4(CUtensorMap *tm, CUtensorMapDataType dt, int esz, void *ba
     const cuuint32_t box[4] = {(cuuint32_t)bx, (cuuint32_t)by, 1u, 3u};
     const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
     return enc(tm, dt, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+               tma_promotion(esz), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 template <class T>
 inline bool make_field_maps(CUtensorMap *cur_box, CUtensorMap *old_box, void *base, int nzp, int ny, int planes, int R) {
@@ -818,7 +831,7 @@ inline bool make_field_maps(CUtensorMap *cur_box, CUtensorMap *old_box, void *ba
 }
 template <class T>
 inline bool make_class_map(CUtensorMap *tm, void *base, int nzp, int ny, int planes, int R) {
-    return make_map3(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, base, nzp, ny, planes, 32 * VecOf<T>::V + 32, R);
+    return make_map3(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, base, nzp, ny, planes, 32 * VecOf<T>::V + 32, R, (int)sizeof(T));
 }
 
 template <class T> inline const char *march_name() { return "march_tma"; }

@@ -1072,7 +1072,7 @@ int phb_create(const phb_cfg *cfg, phb_ctx **out) {
     }
     for (cudaEvent_t *ev : {&c->ev_efork, &c->ev_ejoin, &c->ev_lane, &c->ev_lane_done}) cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
     if (const char *e = getenv("PHB_OVERLAP")) c->overlap = atoi(e) != 0;
-    c->zsplit = cfg->dtype == PHB_F64;      // fp32 has 4 z-tiles: the face tile is a quarter of the grid and the split is indifferent to worse (0.848 vs 0.844 ms)
+    c->zsplit = 1;      // three specialised launches per step (fp64 1.666 -> 1.607 ms, fp32 0.842 -> 0.829 ms at 512^3, with 64-byte TMA promotion)
     if (const char *e = getenv("PHB_ZSPLIT")) c->zsplit = atoi(e);
     if (const char *e = getenv("PHB_FACES_FUSED")) c->faces_fused = atoi(e) != 0;
     cudaEventCreateWithFlags(&c->ev_edge, cudaEventDisableTiming);
