@@ -46,7 +46,9 @@ cfg = {
     "arith": "fast",            # "fast" (<=1e-12 of the reference in fp64) | "exact" (bit-identical, slower) |
                                 # "compensated" (state u, u-u_old: 4-8x less fp32 round-off drift on long runs)
     "device": 0,                # CUDA device ordinal (one process per GPU; slabs via torchrun, see slab_from_env)
-    "record": "surface",        # "surface": uz (and ux, uy) at z-index 0 per step | "full": whole fields | "off"
+    "record": "auto",           # "full": whole fields per step, the reference's schema (base_solver.py:105-133) | "surface": ux, uy,
+                                # uz at z-index 0 only (datasets with z extent 1) | "off" | "auto": full while a frame is at most
+                                # AUTO_FULL_MAX_FRAME_BYTES (the grids the reference's GUI handles), else surface
     "record_every": 1,
     "record_fields": ["ux", "uy", "uz"],   # which displacement components are recorded (the reference writes all three)
     "chunk_steps": 50,          # steps enqueued per library call (cancel / progress granularity)
@@ -179,6 +181,7 @@ class Writer:
 
 
 class Solver:
+    AUTO_FULL_MAX_FRAME_BYTES = 64 << 20     # record = "auto": whole fields up to this frame size (about 140^3 points), surface planes above
     FULL_RING_MAX_FRAME_BYTES = 1 << 30      # record = "full": frames up to this size stream through the recorder ring
     FULL_RING_BYTES = 2 << 30                # pinned + device staging ring budget for them (>= 2 slots)
 
@@ -234,6 +237,13 @@ class Solver:
 
         rec_mode = c["record"] if c.get("write_mode", "off") != "off" else "off"
         x0, nxl, rank, nranks = slab_from_env(x.size) if c.get("slabs_from_env") else (0, x.size, 0, 1)
+        if rec_mode == "auto":
+            # the reference writes the whole fields every step; that is what its consumers index (z_index > 0 in the GUI's
+            # spectrum tab).  Keep that schema wherever it is affordable, fall back to the surface planes on big grids.
+            nf = len([k for k in ("ux", "uy", "uz") if k in c.get("record_fields", ("ux", "uy", "uz"))]) or 1
+            rec_mode = "full" if 8 * x.size * y.size * z.size * nf <= self.AUTO_FULL_MAX_FRAME_BYTES else "surface"
+        if rec_mode not in ("surface", "full", "off"):
+            raise ValueError("cfg['record'] must be 'auto', 'surface', 'full' or 'off' (got %r)" % (c["record"],))
         rec_mask, ring_slots = 0, 32
         fields = tuple(k for k in ("ux", "uy", "uz") if k in c.get("record_fields", ("ux", "uy", "uz")))
         if rec_mode != "off" and not fields:

@@ -203,7 +203,7 @@ DISCOVERY = textwrap.dedent('''
     cfg, g, m = common.loadSettings(path)
     s = common.solver
     assert s.name == "b200" and s.cfg["precision"] == "fp32" and s.cfg["wave"] == settings["simulation"]["cfg"]["wave"]
-    assert s.cfg["record"] == "surface"              # plugin defaults survive the merge (common.py:149-154)
+    assert s.cfg["record"] == "auto"                 # plugin defaults survive the merge (common.py:149-154)
 
     # what BaseSolver.init works with (base_solver.py:194-222): the reference solver on the same objects
     r = common.solver_dict["default"]

@@ -342,3 +342,27 @@ def test_plugin_decimated_volume_snapshots(tmp_path, ring):
     assert np.array_equal(r.read("density"), P[::2, ::3, ::2])
     from tests import h5check
     h5check.validate(s.file)
+
+
+def test_plugin_default_record_mode_is_the_reference_schema_on_small_grids(tmp_path):
+    """cfg["record"] = "auto" (the default): whole fields per step, i.e. exactly what the reference's Writer stores
+    (base_solver.py:105-133, 135-160), while a frame is small; the surface planes only above the size limit."""
+    from phonomena_b200.h5lite import H5Reader
+    d = H.load_golden("testdefaults")
+    nx, ny, nz = d["ids"].shape
+    s = make_solver(d, tmp_path)
+    assert s.cfg["record"] == "auto"
+    s.init(*fake_from_golden(d), d["steps"])
+    s.run()
+    r = H5Reader(s.file)
+    assert r.attrs["record"] == "full" and r.shape("uz") == (nx, ny, nz - 1, d["steps"]) and "elasticity" in r.datasets
+    assert np.array_equal(r.read("ux", frame=d["steps"] - 1), d["ux"])
+    s2 = make_solver(d, tmp_path)
+    s2.AUTO_FULL_MAX_FRAME_BYTES = 0
+    s2.file = str(tmp_path / "big.h5")
+    s2.init(*fake_from_golden(d), d["steps"])
+    s2.run()
+    r2 = H5Reader(s2.file)
+    assert r2.attrs["record"] == "surface" and r2.shape("uz") == (nx, ny, 1, d["steps"])
+    with pytest.raises(ValueError, match="record"):
+        make_solver(d, tmp_path, record="everything").init(*fake_from_golden(d), 3)
