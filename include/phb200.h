@@ -154,6 +154,15 @@ int phb_launch_count(phb_ctx *ctx, int64_t *n);
 /* name of the stencil kernel variant in use, and device bytes allocated */
 int phb_info(phb_ctx *ctx, char *kernel_name, int32_t len, int64_t *device_bytes);
 
+/* Bloch-periodic y boundaries with a phase (beyond the reference, whose archived stubs are the
+ * phase-0 case): u(y + L) = u(y) e^{i phase}, L = ny - 2 rows.  The field is complex = two contexts created with the same
+ * configuration and bc_y = PHB_BC_PERIODIC, `re` and `im`; after pairing, phb_run on `re` steps both (the real stencil
+ * advances each part on its own, the periodic copies mix them with cos / sin of the phase), `im` refuses phb_run.
+ * Set up both parts (spacing, material, abc) before the first step; the source drives the real part only (give `im`
+ * no source table); fields are read from each context with phb_get_fields.  One GPU, not with PHB_COMP.  Destroying
+ * either context dissolves the pair. */
+int phb_bloch_pair(phb_ctx *re, phb_ctx *im, double phase);
+
 /* per-kernel timing of the fused stencil launches (the dominant kernel), for the roofline in
  * bench.py: CUDA event pairs on the launching stream around every stencil launch.
  * Returns the accumulated milliseconds and launch count since profiling was last (re)enabled;

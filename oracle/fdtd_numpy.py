@@ -452,3 +452,58 @@ def build_case(x, y, z, targets, props, primary, secondary, courant, wave="sin",
     dt = cfl_time_step(fdx, fdy, fdz, courant, cp, pp, cs, ps)
     C, P = set_constants(x, y, z, targets, cp, pp, cs, ps)
     return OracleSolver(x, y, z, C, P, dt, wave=wave, wave_args=wave_args, threads=threads)
+
+
+class BlochOracle:
+    """Bloch-periodic y boundaries with a phase, u(y + L) = u(y) exp(i phase), L = ny - 2 rows -- NOT reference behaviour
+    (the reference's archived stubs are the phase-0 case, which OracleSolver(bc_y="periodic") restates and the fixtures
+    pin); this class defines the phase != 0 semantics the device implements so that the two can be compared: the complex
+    field is a real and an imaginary OracleSolver advanced by the reference's real-arithmetic step, coupled only where
+    apply_T_pbc / apply_u_pbc copy: a copy from row ny-2 to row 0 multiplies by exp(-i phase), a copy from row 1 to the
+    last row by exp(+i phase); every product and sum is a separately rounded float64 operation, real part
+    cos*a + sin*b (node rows) / cos*a - sin*b (staggered rows), imaginary part with the sign of sin flipped.
+    The source drives the real part only."""
+
+    def __init__(self, x, y, z, C, P, dt, phase, wave="sin", wave_args=None):
+        self.re = OracleSolver(x, y, z, C, P, dt, wave=wave, wave_args=wave_args, bc_y="periodic")
+        self.im = OracleSolver(x, y, z, C, P, dt, wave=wave, wave_args=wave_args, bc_y="periodic")
+        self.c, self.s = float(np.cos(phase)), float(np.sin(phase))
+        self.dt = dt
+
+    def _mix(self, a, b, s):
+        return self.c * a + s * b
+
+    def step(self):
+        re, im, s = self.re, self.im, self.s
+        w = SOURCES[re.wave](tt=re.tt, dt=re.dt, **re.wave_args)
+        re.uz[0, :, 0] = w
+        for o in (re, im):
+            o.update_T()
+            o.apply_T_tfbc()
+        for name in ("T1", "T2", "T3", "T5"):                      # node rows: row 0 <- row ny-2, exp(-i phase)
+            a, b = getattr(re, name), getattr(im, name)
+            ra, rb = self._mix(a[:, -2, :], b[:, -2, :], s), self._mix(b[:, -2, :], a[:, -2, :], -s)
+            a[:, 0, :], b[:, 0, :] = ra, rb
+        for name in ("T4", "T6"):                                  # staggered rows: last row <- row 1, exp(+i phase)
+            a, b = getattr(re, name), getattr(im, name)
+            ra, rb = self._mix(a[:, 1, :], b[:, 1, :], -s), self._mix(b[:, 1, :], a[:, 1, :], s)
+            a[:, -1, :], b[:, -1, :] = ra, rb
+        for o in (re, im):
+            o.update_u()
+            o.apply_u_tfbc()
+        for name in ("ux_new", "uz_new"):
+            a, b = getattr(re, name), getattr(im, name)
+            ra, rb = self._mix(a[:, -2, :], b[:, -2, :], s), self._mix(b[:, -2, :], a[:, -2, :], -s)
+            a[:, 0, :], b[:, 0, :] = ra, rb
+        a, b = re.uy_new, im.uy_new
+        ra, rb = self._mix(a[:, 1, :], b[:, 1, :], -s), self._mix(b[:, 1, :], a[:, 1, :], s)
+        a[:, -1, :], b[:, -1, :] = ra, rb
+        for o in (re, im):
+            o.apply_u_abc_xz()
+            o.time_step()
+            o.tt += 1
+
+    def run(self, steps):
+        for _ in range(steps):
+            self.step()
+        return self

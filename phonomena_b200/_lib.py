@@ -28,7 +28,7 @@ SYMBOLS = (
     "phb_set_spacing", "phb_set_material_table", "phb_set_material_dense", "phb_set_material_ids", "phb_gen_material_ids",
     "phb_get_material_ids", "phb_set_abc", "phb_set_source_table", "phb_set_fields", "phb_get_fields",
     "phb_get_stress", "phb_run", "phb_sync", "phb_run_timed", "phb_steps_done", "phb_launch_count",
-    "phb_info", "phb_profile", "phb_comm_unique_id", "phb_comm_init", "phb_p2p_export", "phb_p2p_import", "phb_p2p_mode", "phb_record_next", "phb_record_release",
+    "phb_info", "phb_profile", "phb_comm_unique_id", "phb_comm_init", "phb_p2p_export", "phb_p2p_import", "phb_p2p_mode", "phb_bloch_pair", "phb_record_next", "phb_record_release",
     "phb_record_frame_doubles", "phb_record_abort", "phb_record_timeout", "phb_cancel", "phb_writer_start", "phb_writer_mapped", "phb_writer_finish",
     "phb_writer_selftest", "phb_probe_add", "phb_probe_shape", "phb_probe_read", "phb_probe_dft_t", "phb_probe_dft_xt",
 )
@@ -96,6 +96,7 @@ def load_library(path=None):
     lib.phb_p2p_export.argtypes = [vp, C.c_char_p, C.POINTER(C.c_int32)]
     lib.phb_p2p_import.argtypes = [vp, C.c_int32, C.c_int32, C.c_char_p, C.c_int32, C.c_char_p, C.c_int32]
     lib.phb_p2p_mode.argtypes = [vp, C.c_int32]
+    lib.phb_bloch_pair.argtypes = [vp, vp, C.c_double]
     lib.phb_record_next.argtypes = [vp, C.POINTER(dp), C.POINTER(C.c_int64), C.c_int32]
     lib.phb_record_release.argtypes = [vp]
     lib.phb_record_frame_doubles.argtypes = [vp, C.POINTER(C.c_int64)]
@@ -337,6 +338,12 @@ class Engine:
         ms, n = C.c_double(0), C.c_int64(0)
         _chk(self.lib, self.lib.phb_profile(self._ctx, int(enable), C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+    def bloch_pair(self, imag, phase):
+        """Make (self, imag) the real / imaginary part of a Bloch-periodic field with u(y + L) = u(y) exp(i phase);
+        run() on self then steps both (include/phb200.h phb_bloch_pair)."""
+        _chk(self.lib, self.lib.phb_bloch_pair(self._ctx, imag._ctx, float(phase)))
+        self._bloch_imag = imag      # keep the partner alive as long as the primary
 
     # -- multi-GPU ----------------------------------------------------------------------
     def comm_init(self, unique_id, rank, nranks):

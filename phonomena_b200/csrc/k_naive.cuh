@@ -29,11 +29,11 @@ struct StepArgs {
 // u_new for one cell from generic stress evaluations.  Writes only entries the reference's
 // physics writes (App. A.3/A.4 ranges) plus the i = 0 copy that keeps `u_new == u` where
 // nothing is ever written (App. B #9).
-template <class A, class M>
-__device__ __forceinline__ void naive_cell(const StepArgs<typename A::T> &p, const M &m, int i, int j, int k, bool pbc = false) {
+// EV: the stress evaluator (Eval, or EvalBloch for a Bloch-periodic pair of field sets)
+template <class A, class EV>
+__device__ __forceinline__ void naive_cell_ev(const StepArgs<typename A::T> &p, const EV &ev, int i, int j, int k) {
     using T = typename A::T;
     const Geo<T> &g = p.g;
-    Eval<A, M> ev(g, p.cur, m, pbc);
     const bool k0 = (k == 0);
     const long long c = g.idx(i, j, k);
     if (k > g.nz - 2) return;   // k = nz-1: ABC face (ux, uy) / non-existent (uz)
@@ -112,6 +112,12 @@ __device__ __forceinline__ void naive_cell(const StepArgs<typename A::T> &p, con
     }
 }
 
+template <class A, class M>
+__device__ __forceinline__ void naive_cell(const StepArgs<typename A::T> &p, const M &m, int i, int j, int k, bool pbc = false) {
+    Eval<A, M> ev(p.g, p.cur, m, pbc);
+    naive_cell_ev<A>(p, ev, i, j, k);
+}
+
 // grid: x -> k tiles, y -> j tiles, z -> plane (i_begin + blockIdx.z)
 template <class A, class M>
 __global__ void __launch_bounds__(256) k_step_naive(StepArgs<typename A::T> p, M m) {
@@ -150,6 +156,82 @@ __global__ void __launch_bounds__(256) k_pbc_y(StepArgs<typename A::T> p, M m) {
         p.nw.uz[rl] = (i == 0 && k == 0 && p.line_save) ? p.line_save[g.ny - 1] : p.cur.uz[rl];
     }
     p.nw.uy[rm] = p.nw.uy[r1];
+}
+
+// ---------------------------------------------------------------------------------------
+// Bloch-periodic y boundaries with a phase: u(y + L) = u(y) e^{i phi}, L = ny - 2 rows.  The field is complex = two real
+// field sets (a real stencil advances them independently); they couple only where the periodic stubs copy: a copy from
+// row ny-2 to row 0 (node rows: T1, T2, T3, T5, ux, uz) multiplies by e^{-i phi}, a copy from row 1 to the last row
+// (staggered rows: T4, T6, uy) by e^{+i phi}.  phi = 0 is k_pbc_y, i.e. the reference's archived stubs.
+// EvalBloch: evaluator of the set `a` whose wrapped stresses mix in the other set `b`:
+//   node rows:      cph * T_a + sph * T_b        staggered rows:  cph * T_a - sph * T_b
+// (real part: cph = cos phi, sph = sin phi, b = imaginary set; imaginary part: sph = -sin phi, b = real set).
+// ---------------------------------------------------------------------------------------
+template <class A, class M>
+struct EvalBloch {
+    using T = typename A::T;
+    const Geo<T> &g;
+    Eval<A, M> a, b;
+    T cph, sph;
+    __device__ EvalBloch(const Geo<T> &g_, const Fld<T> &ua, const Fld<T> &ub, const M &m, T c_, T s_)
+        : g(g_), a(g_, ua, m, false), b(g_, ub, m, false), cph(c_), sph(s_) {}
+    __device__ __forceinline__ T mix(T x, T y, T s) const { return A::add(A::mul(cph, x), A::mul(s, y)); }
+    __device__ __forceinline__ T coef(int i, int j, int k, int e) const { return a.coef(i, j, k, e); }
+    __device__ __forceinline__ void normal(int i, int j, int k, T &t1, T &t2, T &t3) const {
+        if (j != 0) { a.normal(i, j, k, t1, t2, t3); return; }
+        T x1, x2, x3, y1, y2, y3;
+        a.normal(i, g.ny - 2, k, x1, x2, x3);
+        b.normal(i, g.ny - 2, k, y1, y2, y3);
+        t1 = mix(x1, y1, sph); t2 = mix(x2, y2, sph); t3 = mix(x3, y3, sph);
+    }
+    __device__ __forceinline__ T t5(int i, int j, int k) const {
+        return j != 0 ? a.t5(i, j, k) : mix(a.t5(i, g.ny - 2, k), b.t5(i, g.ny - 2, k), sph);
+    }
+    __device__ __forceinline__ T t4(int i, int j, int k) const {
+        return j != g.ny - 2 ? a.t4(i, j, k) : mix(a.t4(i, 1, k), b.t4(i, 1, k), -sph);
+    }
+    __device__ __forceinline__ T t6(int i, int j, int k) const {
+        return j != g.ny - 2 ? a.t6(i, j, k) : mix(a.t6(i, 1, k), b.t6(i, 1, k), -sph);
+    }
+};
+
+// pa: the real field set (carries the source line), pb: the imaginary one.  threads over (k, i).
+template <class A, class M>
+__global__ void __launch_bounds__(256) k_pbc_y_bloch(StepArgs<typename A::T> pa, StepArgs<typename A::T> pb, M m,
+                                                      typename A::T cph, typename A::T sph) {
+    using T = typename A::T;
+    const Geo<T> &g = pa.g;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = pa.i_begin + blockIdx.y * blockDim.y + threadIdx.y;
+    if (k >= g.nz || i >= pa.i_end) return;
+    EvalBloch<A, M> ea(g, pa.cur, pb.cur, m, cph, sph), eb(g, pb.cur, pa.cur, m, cph, -sph);
+    // the rows the wrapped stresses reach, for both parts, from the CURRENT fields ...
+    naive_cell_ev<A>(pa, ea, i, g.ny - 2, k);
+    naive_cell_ev<A>(pa, ea, i, 0, k);
+    naive_cell_ev<A>(pb, eb, i, g.ny - 2, k);
+    naive_cell_ev<A>(pb, eb, i, 0, k);
+    // ... then the displacement copies with the phase (this thread wrote every value it reads here, or the step kernel did)
+    const long long r0 = g.idx(i, 0, k), r1 = g.idx(i, 1, k), rm = g.idx(i, g.ny - 2, k), rl = g.idx(i, g.ny - 1, k);
+    auto mix = [&](T x, T y, T s) { return A::add(A::mul(cph, x), A::mul(s, y)); };
+    if (i <= g.nx - 2) {
+        const T xa = pa.nw.ux[rm], xb = pb.nw.ux[rm];
+        pa.nw.ux[r0] = mix(xa, xb, sph);
+        pb.nw.ux[r0] = mix(xb, xa, -sph);
+        pa.nw.ux[rl] = pa.cur.ux[rl];
+        pb.nw.ux[rl] = pb.cur.ux[rl];
+    }
+    if (k <= g.nz - 2) {
+        const T xa = pa.nw.uz[rm], xb = pb.nw.uz[rm];
+        pa.nw.uz[r0] = mix(xa, xb, sph);
+        pb.nw.uz[r0] = mix(xb, xa, -sph);
+        pa.nw.uz[rl] = (i == 0 && k == 0 && pa.line_save) ? pa.line_save[g.ny - 1] : pa.cur.uz[rl];
+        pb.nw.uz[rl] = (i == 0 && k == 0 && pb.line_save) ? pb.line_save[g.ny - 1] : pb.cur.uz[rl];
+    }
+    {
+        const T ya = pa.nw.uy[r1], yb = pb.nw.uy[r1];
+        pa.nw.uy[rm] = mix(ya, yb, -sph);
+        pb.nw.uy[rm] = mix(yb, ya, sph);
+    }
 }
 
 // Stress dump in the reference's array shapes (double), for phb_get_stress.

@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -112,6 +113,10 @@ struct IEngine {
     virtual int step() = 0;
     virtual int make_maps() = 0;
     virtual const char *kernel_name() = 0;
+    // Bloch pair: the follower's share of a step, launched by the primary on the primary's streams
+    virtual int follower_physics() = 0;
+    virtual int follower_faces() = 0;
+    virtual void advance() = 0;
 };
 
 struct phb_ctx {
@@ -196,6 +201,11 @@ struct phb_ctx {
     // line probes (k_probe.cuh)
     struct Probe { int comp, j, k, rows; long long cap, frames; double *trace; };
     std::vector<Probe> probes;
+    // Bloch-periodic pair (phb_bloch_pair): the real part (role 1) steps both contexts; the imaginary part (role 2) follows
+    phb_ctx *partner = nullptr;
+    int bloch_role = 0;
+    double bloch_c = 1.0, bloch_s = 0.0;
+    cudaEvent_t ev_pair = nullptr;
     IEngine *eng = nullptr;
     std::mutex mu;
 };
@@ -421,6 +431,7 @@ struct Engine : IEngine {
 
     int stress(int which, double *Th[6]) override {
         if (!c->have_spacing || !c->code) return fail("spacing/material not set");
+        if (c->bloch_role) return fail("the stress dump is not available for a Bloch pair (the wrapped stresses mix both parts)");
         const int b = which == PHB_CUR ? b_cur() : b_old();
         const int nx = c->cfg.nx, ny = c->cfg.ny, nz = c->cfg.nz;
         const int n = c->cfg.nxl, n5 = owned_planes(0);
@@ -681,7 +692,7 @@ struct Engine : IEngine {
     // periodic y boundaries: recompute the rows the wrapped stresses reach + the displacement copies (k_pbc_y); must run
     // right after the stencil launch of the same planes, BEFORE the x face (the reference order: pbc, then apply_u_abc)
     int pbc_y(int ib, int ie) {
-        if (ie <= ib || !periodic_y()) return 0;
+        if (ie <= ib || !periodic_y() || c->bloch_role) return 0;      // (a Bloch pair runs k_pbc_y_bloch once for both parts)
         StepArgs<T> p;
         for (int q = 0; q < 3; ++q) p.push_lo[q] = p.push_hi[q] = nullptr;
         p.edge_b = -1; p.zface = 0; p.ztile0 = 0;
@@ -774,20 +785,81 @@ struct Engine : IEngine {
             if (c->gexec[ph]) {
                 CU(cudaGraphLaunch(c->gexec[ph], c->st));
                 c->launches += c->gnodes[ph];
-                c->cur = b_new();
-                c->tt++;
+                advance();
+                if (c->bloch_role == 1) c->partner->eng->advance();
                 return 0;
             }
         }
         OK(launch_step());
         c->plain_steps++;
-        c->cur = b_new();   // rotate: old <- cur, cur <- new
+        advance();          // rotate: old <- cur, cur <- new
+        if (c->bloch_role == 1) c->partner->eng->advance();
+        return 0;
+    }
+    void advance() override {
+        c->cur = b_new();
         c->tt++;
+    }
+    // ---- Bloch pair ------------------------------------------------------------------------------------------
+    // The follower's launches go to the PRIMARY's streams (program order = execution order, and the primary's CUDA graph
+    // of the step contains them): its stream / event handles are swapped for the primary's for the duration of the call.
+    struct StreamSwap {
+        phb_ctx *f, *p;
+        cudaStream_t st, zst, kst, est, ezst;
+        cudaEvent_t a, b, k;
+        StreamSwap(phb_ctx *f_, phb_ctx *p_) : f(f_), p(p_), st(f_->st), zst(f_->zst), kst(f_->kst), est(f_->est), ezst(f_->ezst),
+                                               a(f_->ev_fork), b(f_->ev_join), k(f_->ev_kjoin) {
+            f->st = p->st; f->zst = p->zst; f->kst = p->kst; f->est = p->est; f->ezst = p->ezst;
+            f->ev_fork = p->ev_fork; f->ev_join = p->ev_join; f->ev_kjoin = p->ev_kjoin;
+        }
+        ~StreamSwap() { f->st = st; f->zst = zst; f->kst = kst; f->est = est; f->ezst = ezst; f->ev_fork = a; f->ev_join = b; f->ev_kjoin = k; }
+    };
+    int follower_physics() override {
+        StreamSwap sw(c, c->partner);
+        return physics(c->cfg.x0, c->cfg.x0 + c->cfg.nxl);
+    }
+    int follower_faces() override {
+        StreamSwap sw(c, c->partner);
+        return faces(c->cfg.x0, c->cfg.x0 + c->cfg.nxl, true);
+    }
+    StepArgs<T> pbc_args() {
+        StepArgs<T> p;
+        for (int q = 0; q < 3; ++q) p.push_lo[q] = p.push_hi[q] = nullptr;
+        p.edge_b = -1; p.zface = 0; p.ztile0 = 0;
+        p.zf_cl = p.zf_ct = (T)0;
+        p.g = geo();
+        p.cur = fld(b_cur()); p.old = fld(b_old()); p.nw = fld(b_new());
+        p.line_save = (c->w && c->cfg.x0 == 0) ? (const T *)c->line_save : nullptr;
+        p.i_begin = c->cfg.x0; p.i_end = c->cfg.x0 + c->cfg.nxl;
+        return p;
+    }
+    int launch_step_bloch() {
+        auto *fe = static_cast<Engine<T> *>(c->partner->eng);
+        const int x0 = c->cfg.x0, xe = x0 + c->cfg.nxl;
+        if (c->w) {
+            k_source<T><<<1, 256, 0, c->st>>>(geo(), (T *)c->buf[b_cur()][2], (T *)c->line_save, c->w, c->src_idx);
+            c->launches++;
+        }
+        OK(physics(x0, xe));
+        OK(fe->follower_physics());
+        {
+            StepArgs<T> pa = pbc_args(), pb = fe->pbc_args();
+            MatCls<T> m = mat();
+            dim3 bl = block_for(c->cfg.nz), gr = grid3(c->cfg.nz, xe - x0, 1, bl);
+            if (c->cfg.arith == PHB_EXACT) k_pbc_y_bloch<Ar<T, true>, MatCls<T>><<<gr, bl, 0, c->st>>>(pa, pb, m, (T)c->bloch_c, (T)c->bloch_s);
+            else k_pbc_y_bloch<Ar<T, false>, MatCls<T>><<<gr, bl, 0, c->st>>>(pa, pb, m, (T)c->bloch_c, (T)c->bloch_s);
+            c->launches++;
+            CU(cudaGetLastError());
+        }
+        OK(faces(x0, xe, true));
+        OK(fe->follower_faces());
         return 0;
     }
 
     // the launches of one time step on c->st (does not advance tt / rotate)
     int launch_step() {
+        if (c->bloch_role == 2) return fail("this context is the imaginary part of a Bloch pair: run the real part");
+        if (c->bloch_role == 1) return launch_step_bloch();
         const int x0 = c->cfg.x0, xe = c->cfg.x0 + c->cfg.nxl;
         const bool last = (xe == c->cfg.nx);
         if (c->w && x0 == 0) {
@@ -1135,8 +1207,19 @@ int phb_destroy(phb_ctx *c) {
     if (!c) return 0;
     // writer threads read the pinned ring: stop and join them before anything is freed (a context destroyed with a
     // live consumer was a use-after-free); a caller blocked in phb_record_next sees the abort and returns
+    if (c->partner) {           // unlink a Bloch pair: the other part becomes an ordinary periodic context again
+        cudaStreamSynchronize(c->st);
+        if (c->partner->st) cudaStreamSynchronize(c->partner->st);
+        graph_invalidate(c->partner);
+        c->partner->partner = nullptr;
+        c->partner->bloch_role = 0;
+        c->partner = nullptr;
+    }
+    if (c->ev_pair) cudaEventDestroy(c->ev_pair);
     c->rec.abort("context destroyed");
     c->wr.finish(2000);
+    for (int spins = 0; c->rec.in_api.load() > 0 && spins < 40000; ++spins)      // a consumer inside phb_record_next sees the abort and leaves (<= 2 s)
+        std::this_thread::sleep_for(std::chrono::microseconds(50));
     cudaSetDevice(c->device);
     if (c->st) cudaStreamSynchronize(c->st);
     if (c->cst) cudaStreamSynchronize(c->cst);
@@ -1389,6 +1472,21 @@ static int run_locked(phb_ctx *c, int64_t nsteps) {
     if (!c->have_abc) return fail("phb_set_abc not called");
     if (c->nranks > 1 && !c->comm && c->halo != 2) return fail("slab context without halo exchange: call phb_comm_init or phb_p2p_import");
     if (c->cfg.record_mask && c->rec.aborted.load()) return fail("recording aborted: %s", c->rec.why().c_str());
+    if (c->bloch_role == 2) return fail("this context is the imaginary part of a Bloch pair: run the real part");
+    if (c->bloch_role == 1) {        // whatever the follower has queued on its own stream (field uploads) comes first
+        if (c->partner->tt != c->tt || c->partner->cur != c->cur) return fail("Bloch pair out of step");
+        CU(cudaEventRecord(c->ev_pair, c->partner->st));
+        CU(cudaStreamWaitEvent(c->st, c->ev_pair, 0));
+    }
+    struct PairJoin {      // ... and what the follower does next on its own stream (field downloads) waits for this run
+        phb_ctx *c;
+        ~PairJoin() {
+            if (c->bloch_role == 1 && c->partner) {
+                cudaEventRecord(c->ev_pair, c->st);
+                cudaStreamWaitEvent(c->partner->st, c->ev_pair, 0);
+            }
+        }
+    } pair_join{c};
     for (int64_t s = 0; s < nsteps; ++s) {
         if (c->cancel.load()) {        // phb_cancel from another thread (BaseSolver.cancel, base_solver.py:246-248,282-284)
             c->cancel.store(0);
@@ -1551,6 +1649,30 @@ int phb_p2p_import(phb_ctx *c, int32_t rank, int32_t nranks, const char *left, i
     return 0;
 }
 
+int phb_bloch_pair(phb_ctx *re, phb_ctx *im, double phase) {
+    if (!re || !im || re == im) return fail("two distinct contexts are needed");
+    std::lock_guard<std::mutex> l1(re->mu);
+    std::lock_guard<std::mutex> l2(im->mu);
+    const phb_cfg &a = re->cfg, &b = im->cfg;
+    if (a.nx != b.nx || a.ny != b.ny || a.nz != b.nz || a.x0 != b.x0 || a.nxl != b.nxl || a.dtype != b.dtype || a.arith != b.arith ||
+        a.kernel != b.kernel || a.device != b.device)
+        return fail("the two parts of a Bloch pair must be created with the same grid, type, arithmetic, kernel and device");
+    if (a.bc_y != PHB_BC_PERIODIC || b.bc_y != PHB_BC_PERIODIC) return fail("both parts must be created with bc_y = PHB_BC_PERIODIC");
+    if (a.x0 != 0 || a.nxl != a.nx || re->nranks > 1 || im->nranks > 1) return fail("a Bloch pair runs on one GPU (whole grid)");
+    if (re->partner || im->partner) return fail("context already paired");
+    if (re->tt != 0 || im->tt != 0) return fail("pair the contexts before the first step");
+    if (im->cfg.record_mask) return fail("the imaginary part cannot record (read it with phb_get_fields)");
+    CU(cudaSetDevice(re->device));
+    if (!re->ev_pair) CU(cudaEventCreateWithFlags(&re->ev_pair, cudaEventDisableTiming));
+    graph_invalidate(re);
+    graph_invalidate(im);
+    re->partner = im; im->partner = re;
+    re->bloch_role = 1; im->bloch_role = 2;
+    re->bloch_c = im->bloch_c = cos(phase);
+    re->bloch_s = im->bloch_s = sin(phase);
+    return 0;
+}
+
 int phb_p2p_mode(phb_ctx *c, int32_t fused_in_kernel) {
     ENTER(c);
     graph_invalidate(c);
@@ -1564,8 +1686,14 @@ int phb_record_frame_doubles(phb_ctx *c, int64_t *n) {
     *n = c->rec.frame_doubles;
     return 0;
 }
+struct InApi {      // marks a consumer call in progress so that phb_destroy does not free the ring under it
+    std::atomic<int> &n;
+    explicit InApi(std::atomic<int> &n_) : n(n_) { n.fetch_add(1); }
+    ~InApi() { n.fetch_sub(1); }
+};
 int phb_record_next(phb_ctx *c, const double **frame, int64_t *tt, int32_t timeout_ms) {
     if (!c || !c->rec.host) return fail("recording not enabled");
+    InApi guard(c->rec.in_api);
     if (c->wr.started) return fail("the native writer is draining the ring (phb_writer_start)");
     RecRing &r = c->rec;
     if (r.consumed.load() != r.released.load()) return fail("previous frame not released");

@@ -41,6 +41,7 @@ struct RecRing {
     std::vector<char> slot_done;       // native writer: slot written, waiting for in-order release
     std::atomic<long long> produced{0}, consumed{0}, released{0};
     std::atomic<int> aborted{0};
+    std::atomic<int> in_api{0};        // consumer threads currently inside phb_record_next / phb_record_release (phb_destroy waits for 0)
     std::atomic<int> timeout_ms{120000};   // producer: longest wait for a free slot (reference: queue timeout 120 s)
     std::mutex mu;                     // abort message, in-order release
     std::string abort_msg;

@@ -58,7 +58,9 @@ cfg = {
     "record_stride": [1, 1, 1], # record = "full": keep every sx-th plane / sy-th row / sz-th level (decimated volume snapshots of big grids)
     "merge_slabs": True,        # multi-GPU: concatenate the per-slab files into `file` after the run (rank 0)
     "bc_y": "absorbing",        # "absorbing": Mur faces at y = 0 / y = -1 (the reference) | "periodic": the reference's archived
-                                # apply_T_pbc / apply_u_pbc stubs (zero Bloch phase) in their place
+                                # apply_T_pbc / apply_u_pbc stubs (zero Bloch phase) in their place | "bloch": the
+                                # same with a phase, u(y + L) = u(y) exp(i bloch_phase): complex field, two device contexts
+    "bloch_phase": 0.0,         # radians (bc_y = "bloch")
     "probes": [],               # [{"u": "uz", "y": j, "z": k}, ...]: (x, t) lines kept on the device for Solver.spectrum()
 }
 
@@ -273,8 +275,15 @@ class Solver:
                         dtype={"fp64": "f64", "fp32": "f32"}[c["precision"]], arith=c["arith"],
                         device=int(c["device"]), x0=x0, nxl=nxl, kernel=c.get("kernel", "auto"),
                         record_mask=rec_mask, record_every=int(c["record_every"]), ring_slots=ring_slots,
-                        bc_y=c.get("bc_y", "absorbing"), record_stride=stride)
+                        bc_y={"bloch": "periodic"}.get(c.get("bc_y", "absorbing"), c.get("bc_y", "absorbing")), record_stride=stride)
         self.engine = e
+        self.engine_imag = None
+        if c.get("bc_y") == "bloch":
+            if nranks > 1:
+                raise ValueError("bc_y = 'bloch' runs on one GPU")
+            # the imaginary part: same grid / material / faces, no source, no recorder; paired below
+            self.engine_imag = _lib.Engine(x.size, y.size, z.size, dt, d2=dt ** 2, dtype={"fp64": "f64", "fp32": "f32"}[c["precision"]],
+                                           arith=c["arith"], device=int(c["device"]), kernel=c.get("kernel", "auto"), bc_y="periodic")
         if nranks > 1:
             # one process per GPU: fused NVLink halo push (CUDA IPC handles all-gathered over any host channel,
             # default torch.distributed), NCCL send/recv as fallback
@@ -300,6 +309,16 @@ class Solver:
                 corner = int(self.broadcast(corner if rank == 0 else None))
             cm = sec if corner else prim
         e.set_abc(hm.abc_coefficients(cm["c"], cm["p"], dt, fdx, fdy, fdz, sdx, sdy, sdz))
+        if self.engine_imag is not None:
+            ei = self.engine_imag
+            ei.set_spacing(fdx, fdy, fdz, sdx, sdy, sdz)
+            if dense:
+                ei.set_material_dense(Cd[sl], Pd[sl])
+            else:
+                ei.set_material_table([prim["c"], sec["c"]], [prim["p"], sec["p"]])
+                ei.gen_material_ids(targets, mx, my, mz)
+            ei.set_abc(hm.abc_coefficients(cm["c"], cm["p"], dt, fdx, fdy, fdz, sdx, sdy, sdz))
+            e.bloch_pair(ei, float(c.get("bloch_phase", 0.0)))
         self.dt, self._x0 = dt, x0
         self._x, self._fdx, self._nranks = x, fdx, nranks
         # line probes: the (x, t) matrices analysis.spectrum would re-read from the file stay in HBM
@@ -474,8 +493,15 @@ class Solver:
 
     # -- helpers for tests / scripts -----------------------------------------------------------
     def fields(self):
-        """(ux, uy, uz) of the current state in the reference's shapes."""
+        """(ux, uy, uz) of the current state in the reference's shapes (bc_y = "bloch": the real part)."""
         return self.engine.get_fields()
+
+    def fields_imag(self):
+        """bc_y = "bloch": the imaginary part of the current state."""
+        if getattr(self, "engine_imag", None) is None:
+            raise RuntimeError("no imaginary part: cfg['bc_y'] is not 'bloch'")
+        self.engine.sync()
+        return self.engine_imag.get_fields()
 
     def _close_engine(self):
         if self.writer is not None:
@@ -484,6 +510,9 @@ class Solver:
         if self.engine is not None:
             self.engine.close()
             self.engine = None
+        if getattr(self, "engine_imag", None) is not None:
+            self.engine_imag.close()
+            self.engine_imag = None
 
     def __del__(self):
         try:

@@ -81,3 +81,73 @@ def test_periodic_y_plugin_cfg_and_errors(tmp_path):
         H.engine_from_golden(d, arith="compensated", dtype="f32", bc_y="periodic")
     with pytest.raises(KeyError):
         H.engine_from_golden(d, bc_y="bloch")
+
+
+# ---- Bloch phase (beyond the reference: its archived stubs are the phase-0 case) -------------------------------------
+def _bloch_engines(d, phase, dtype="f64", arith="exact", kernel="auto"):
+    re = H.engine_from_golden(d, dtype=dtype, arith=arith, kernel=kernel, bc_y="periodic")
+    im = H.engine_from_golden(d, dtype=dtype, arith=arith, kernel=kernel, bc_y="periodic")
+    im.set_source_table(None)
+    re.bloch_pair(im, phase)
+    return re, im
+
+
+@pytest.mark.parametrize("kernel", ["naive", "march"])
+def test_bloch_phase_zero_is_the_reference_periodic_case(kernel):
+    """phase = 0: the real part of a Bloch pair is bit-identical to the reference-with-stubs fixture, the imaginary part
+    stays exactly zero."""
+    d = H.load_golden("periodic_y_crystal_40x18x14")
+    re, im = _bloch_engines(d, 0.0, kernel=kernel)
+    re.run(d["steps"])
+    re.sync()
+    for got, key in zip(re.get_fields(), ("ux", "uy", "uz")):
+        assert np.array_equal(got, d[key]), key
+    assert all(not a.any() for a in im.get_fields())
+    with pytest.raises(Exception, match="imaginary part"):
+        im.run(1)
+    im.close()
+    re.close()
+
+
+@pytest.mark.parametrize("phase", [0.7, np.pi, -2.1])
+def test_bloch_phase_vs_oracle(phase):
+    """phase != 0: the device against oracle.fdtd_numpy.BlochOracle (which DEFINES these semantics; parity unpinned by
+    the reference, which has no phase) -- EXACT arithmetic bit for bit in both parts, FAST <= 1e-12, fp32 <= 1e-5; and the
+    Bloch relation itself: the periodic rows of the complex field differ by exp(-+ i phase)."""
+    from oracle import fdtd_numpy as onp
+    d = H.load_golden("periodic_y_crystal_40x18x14")
+    steps = 90
+    t = H.targets_of(d)
+    C, P = onp.set_constants(d["x"], d["y"], d["z"], t, d["prim_c"], d["prim_p"], d["sec_c"], d["sec_p"])
+    o = onp.BlochOracle(d["x"], d["y"], d["z"], C, P, d["dt"], phase, wave=d["wave"], wave_args=d["wave_args"]).run(steps)
+    ref_re, ref_im = [o.re.ux, o.re.uy, o.re.uz], [o.im.ux, o.im.uy, o.im.uz]
+    assert sum(float(np.abs(a).sum()) for a in ref_im) > 0           # the phase really couples the parts
+    for kernel in ("march", "naive"):
+        re, im = _bloch_engines(d, phase, kernel=kernel)
+        re.run(steps)
+        re.sync()
+        got_re, got_im = re.get_fields(), im.get_fields()
+        im.close(); re.close()
+        for a, b, n in zip(got_re + got_im, ref_re + ref_im, ("ux", "uy", "uz", "ux_im", "uy_im", "uz_im")):
+            assert np.array_equal(a, b), (kernel, n, float(np.abs(a - b).max()))
+    z = got_re[0] + 1j * got_im[0]                                    # ux: row 0 = exp(-i phase) * row ny-2 (off the z face)
+    assert np.allclose(z[:, 0, :-1], np.exp(-1j * phase) * z[:, -2, :-1], rtol=1e-12, atol=1e-300)
+    for dtype, arith, tol in (("f64", "fast", 1e-12), ("f32", "fast", 1e-5)):
+        re, im = _bloch_engines(d, phase, dtype=dtype, arith=arith)
+        re.run(steps)
+        re.sync()
+        assert H.rel_l2(re.get_fields() + im.get_fields(), ref_re + ref_im) <= tol, (dtype, arith)
+        im.close(); re.close()
+
+
+def test_bloch_plugin_cfg(tmp_path):
+    from oracle import fdtd_numpy as onp
+    from tests.test_gpu_plugin import fake_from_golden, make_solver
+    d = H.load_golden("periodic_y_homog_24x12x10")
+    s = make_solver(d, tmp_path, write_mode="off", bc_y="bloch", bloch_phase=1.1)
+    s.init(*fake_from_golden(d), 40)
+    s.run()
+    C, P = onp.set_constants(d["x"], d["y"], d["z"], H.targets_of(d), d["prim_c"], d["prim_p"], d["sec_c"], d["sec_p"])
+    o = onp.BlochOracle(d["x"], d["y"], d["z"], C, P, d["dt"], 1.1, wave=d["wave"], wave_args=d["wave_args"]).run(40)
+    for a, b in zip(s.fields() + s.fields_imag(), [o.re.ux, o.re.uy, o.re.uz, o.im.ux, o.im.uy, o.im.uz]):
+        assert np.array_equal(a, b)

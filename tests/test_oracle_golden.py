@@ -147,3 +147,23 @@ def test_periodic_y_oracle_matches_reference_stubs(name):
     assert not np.array_equal(a.uz, o.uz)
     assert np.array_equal(o.ux[:, 0, :-1], o.ux[:, -2, :-1]) and np.array_equal(o.uy[:, -1, :-1], o.uy[:, 1, :-1])
     assert np.array_equal(o.uz[:, 0, :-1], o.uz[:, -2, :-1])
+
+
+@pytest.mark.parametrize("name", H.periodic_names())
+def test_bloch_oracle_phase_zero_is_pinned_by_the_reference_stubs(name):
+    """BlochOracle defines the phase != 0 semantics (no reference behaviour exists for it); at phase 0 it must collapse to
+    the reference-with-stubs fixtures bit for bit, with an identically zero imaginary part -- and for phase != 0 the
+    complex field obeys the Bloch relation on the periodic rows."""
+    d = H.load_golden(name)
+    t = H.targets_of(d)
+    C, P = onp.set_constants(d["x"], d["y"], d["z"], t, d["prim_c"], d["prim_p"], d["sec_c"], d["sec_p"])
+    o = onp.BlochOracle(d["x"], d["y"], d["z"], C, P, d["dt"], 0.0, wave=d["wave"], wave_args=d["wave_args"]).run(d["steps"])
+    for k in ("ux", "uy", "uz", "ux_old", "uy_old", "uz_old"):
+        assert np.array_equal(getattr(o.re, k), d[k]), (name, k)
+        assert not getattr(o.im, k).any()
+    phase = 0.9
+    o = onp.BlochOracle(d["x"], d["y"], d["z"], C, P, d["dt"], phase, wave=d["wave"], wave_args=d["wave_args"]).run(min(d["steps"], 60))
+    z = o.re.ux + 1j * o.im.ux
+    assert np.abs(o.im.uz).max() > 0 and np.allclose(z[:, 0, :-1], np.exp(-1j * phase) * z[:, -2, :-1], rtol=1e-12, atol=1e-300)
+    zy = o.re.uy + 1j * o.im.uy
+    assert np.allclose(zy[:, -1, :-1], np.exp(1j * phase) * zy[:, 1, :-1], rtol=1e-12, atol=1e-300)
