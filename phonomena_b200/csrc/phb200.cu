@@ -137,7 +137,7 @@ struct phb_ctx {
     int overlap = 0;                   // PHB_OVERLAP=1: edge x-chunks on their own lane behind the flag wait, middle chunks ungated
                                        // (measured at 2 GPUs, 512 planes each: 1.706 vs 1.693 ms -- the two extra x-chunks cost more
                                        // than the hidden wait saves; kept as an opt-in, tested bit-identical)
-    int zsplit = 1;                    // PHB_ZSPLIT=0: one launch for all z-tiles
+    int zsplit = -1;                   // PHB_ZSPLIT: 0 one launch for all z-tiles, 1 three specialised launches, 2 face tile + rest, -1 auto
     int faces_fused = 1;               // PHB_FACES_FUSED=0: ordered x, y, z face launches even when the z face is fused into the stencil
     cudaEvent_t ev_edge = nullptr, ev_comm = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
     void *buf[3][3] = {};      // [buffer][component], each (nxl+2) planes
@@ -535,10 +535,14 @@ struct Engine : IEngine {
                 // own with the face instantiation, on a second (higher-priority) stream beside the launch for all other
                 // z-tiles without it; both finish inside the same waves of blocks.
                 const int V = VecOf<T>::V, nzt = (c->nzp + 32 * V - 1) / (32 * V);
-                if (p.zface == 1 && c->zsplit && nzt >= 2 && (edge_b < 0 || ie - ib >= 16) && c->mR == 16 && c->mNST == 4 && c->mRW == 2) {
+                // auto: a wide cross-section (>= 200 k cells, i.e. every part fills its waves) and, for fp32, a long step
+                const long long yz_cells = (long long)c->cfg.ny * c->cfg.nz;
+                const bool want_split = c->zsplit > 0 || (c->zsplit < 0 && yz_cells >= 200000 &&
+                                                          (sizeof(T) == 8 || (long long)(ie - ib) * yz_cells >= 100000000LL));
+                if (p.zface == 1 && want_split && nzt >= 2 && (edge_b < 0 || ie - ib >= 16) && c->mR == 16 && c->mNST == 4 && c->mRW == 2) {
                     // parts: [face tile: ZF instantiation] [tile 0: with the k = 0 selects] [tiles between: neither] -- the
                     // middle part is the bulk and stays on the lane's main stream; PHB_ZSPLIT=2: face tile + the rest (round 2a)
-                    const bool three = c->zsplit == 1 && nzt >= 3 && lane == 0;
+                    const bool three = c->zsplit != 2 && nzt >= 3 && lane == 0;
                     CU(cudaEventRecord(EF, S));
                     CU(cudaStreamWaitEvent(ZS, EF, 0));
                     StepArgs<T> pz = p;
@@ -1144,7 +1148,11 @@ int phb_create(const phb_cfg *cfg, phb_ctx **out) {
     }
     for (cudaEvent_t *ev : {&c->ev_efork, &c->ev_ejoin, &c->ev_lane, &c->ev_lane_done}) cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
     if (const char *e = getenv("PHB_OVERLAP")) c->overlap = atoi(e) != 0;
-    c->zsplit = 1;      // three specialised launches per step (fp64 1.666 -> 1.607 ms, fp32 0.842 -> 0.829 ms at 512^3, with 64-byte TMA promotion)
+    // three specialised launches per step (fp64 1.666 -> 1.607 ms, fp32 0.842 -> 0.829 ms at 512^3, with 64-byte TMA promotion) -- but
+    // only where the two extra launches and their fork / join (~10-15 us) pay: measured on a 512 x 512 cross-section fp64 gains down
+    // to 128-plane slabs (0.4345 vs 0.4379 ms), fp32 only at 512 planes (256: 0.445 vs 0.430); on 384^2 / 320^2 cross-sections the
+    // parts no longer fill their waves (320^3: 0.471 vs 0.447 ms) -> auto, see physics()
+    c->zsplit = -1;
     if (const char *e = getenv("PHB_ZSPLIT")) c->zsplit = atoi(e);
     if (const char *e = getenv("PHB_FACES_FUSED")) c->faces_fused = atoi(e) != 0;
     cudaEventCreateWithFlags(&c->ev_edge, cudaEventDisableTiming);
