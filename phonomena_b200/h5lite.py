@@ -122,6 +122,23 @@ class H5Writer:
         addr = self._append(a.tobytes()) if a.size else UNDEF
         self._contig.append((name, a.shape, addr, a.nbytes))
 
+    def create_dataset_from(self, name, shape, pieces):
+        """Contiguous float64 dataset of `shape` written piece by piece (an iterable of arrays that concatenate, in C
+        order, to the whole): the 1 GB `density` of a 512^3 grid never exists as one host array nor as a bytes copy."""
+        shape = tuple(int(v) for v in shape)
+        nbytes = int(np.prod(shape)) * 8
+        with self._lock:
+            addr = self._end + (-self._end % 8)
+            self._end = addr + nbytes
+        pos = addr
+        for a in pieces:
+            a = np.ascontiguousarray(np.asarray(a, dtype="<f8"))
+            self._pwrite(a.reshape(-1).data, pos)
+            pos += a.nbytes
+        if pos != addr + nbytes:
+            raise ValueError("dataset %s: pieces hold %d bytes, shape %s needs %d" % (name, pos - addr, shape, nbytes))
+        self._contig.append((name, shape, addr if nbytes else UNDEF, nbytes))
+
     def settle(self):
         """Flush what has been written so far to the device (used after the large static datasets)."""
         try:

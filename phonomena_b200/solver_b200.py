@@ -101,7 +101,11 @@ class Writer:
         self.h5.attrs.update(meta["attrs"])
         self.h5.attrs["record_every"] = int(record_every)
         self.h5.attrs["record"] = mode
-        self.h5.create_dataset("density", meta["density"])
+        if callable(meta["density"]):          # (shape, piece iterator): written plane block by plane block
+            dshape, pieces = meta["density"]()
+            self.h5.create_dataset_from("density", dshape, pieces)
+        else:
+            self.h5.create_dataset("density", meta["density"])
         if meta.get("elasticity") is not None:
             self.h5.create_dataset("elasticity", meta["elasticity"])
         ny, nz = engine.ny, engine.nz
@@ -331,7 +335,16 @@ class Solver:
         self.writer = None
         if rec_mode != "off":
             frames = self.t // int(c["record_every"])
-            P = P_out if dense else np.where(ids == 1, sec["p"], prim["p"]).astype(np.float64)
+            if dense:
+                P = P_out
+            else:
+                # density = table[id]: produced plane block by plane block while it is written (a 512^3 grid would otherwise
+                # need a 1 GB float64 array plus a bytes copy of it: most of init()'s time)
+                lut = np.array([prim["p"], sec["p"]], np.float64)
+                ids_d = ids[::stride[0], ::stride[1], ::stride[2]] if stride != (1, 1, 1) else ids
+
+                def P(ids_d=ids_d, lut=lut):
+                    return ids_d.shape, (lut[ids_d[q:q + 16]] for q in range(0, ids_d.shape[0], 16))
             attrs = {"x": x, "y": y, "z": z,
                      "sdx": sdx.reshape(-1, 1, 1), "sdy": sdy.reshape(1, -1, 1), "sdz": sdz.reshape(1, 1, -1),
                      "fdx": fdx.reshape(-1, 1, 1), "fdy": fdy.reshape(1, -1, 1), "fdz": fdz.reshape(1, 1, -1),
@@ -347,9 +360,11 @@ class Solver:
                     fd = np.diff(line) * si
                     attrs[key] = fd.reshape(shp)
                     attrs["s" + key[1:]] = (0.5 * (fd[1:] + fd[:-1])).reshape(shp)
-                P = np.ascontiguousarray(P[::sx_, ::sy_, ::sz_])
+                if dense:
+                    P = np.ascontiguousarray(P[::sx_, ::sy_, ::sz_])
             meta = {"attrs": attrs, "density": P, "elasticity": None}
-            if rec_mode == "full" and P.size <= 1 << 22:      # the reference's `elasticity` is 288 B/cell
+            n_density = (ids[::stride[0], ::stride[1], ::stride[2]].size if not dense else P.size)
+            if rec_mode == "full" and n_density <= 1 << 22:      # the reference's `elasticity` is 288 B/cell
                 Cfull = np.array(C_out, np.float64) if dense else np.where((ids == 1)[..., None, None], sec["c"], prim["c"])
                 meta["elasticity"] = np.ascontiguousarray(Cfull[::stride[0], ::stride[1], ::stride[2]])
             path = self.file if nranks == 1 else "%s.rank%d" % (self.file, rank)      # one file per slab

@@ -325,3 +325,23 @@ def test_native_ring_flow_control_and_threads(tmp_path):
             a = raw[(base[0] + f * stride) // 8:][:24]
             b = raw[(base[1] + f * stride) // 8:][:40]
             assert np.array_equal(a, f * 1e6 + np.arange(24)) and np.array_equal(b, f * 1e6 + 24 + np.arange(40)), (nthreads, f)
+
+
+def test_h5writer_dataset_from_pieces(tmp_path):
+    """H5Writer.create_dataset_from: a contiguous dataset streamed in plane blocks equals the one written at once, and a
+    short iterator is an error, not a silently truncated dataset."""
+    from phonomena_b200.h5lite import H5Reader, H5Writer
+    from tests import h5check
+    rng = np.random.default_rng(4)
+    a = rng.standard_normal((37, 5, 6))
+    p = str(tmp_path / "pieces.h5")
+    with H5Writer(p) as w:
+        w.create_dataset_from("density", a.shape, (a[q:q + 16] for q in range(0, 37, 16)))
+        w.create_dataset("other", a[:3])
+        w.attrs["dt"] = 1.0
+    r = H5Reader(p)
+    assert np.array_equal(r.read("density"), a) and np.array_equal(r.read("other"), a[:3])
+    h5check.validate(p)
+    w = H5Writer(str(tmp_path / "short.h5"))
+    with pytest.raises(ValueError, match="pieces"):
+        w.create_dataset_from("density", a.shape, (a[q:q + 16] for q in range(0, 32, 16)))
