@@ -1,6 +1,6 @@
 #!/bin/bash
 # final single-GPU artefacts of round 2: long run, bench lines (f64 default, f32, reference arm), launch list
-# (the ncu --set full captures are separate calls, tools/gpu_r2q.sh f64|f32: gpurun copies back at most 64 MiB per call)
+# (the ncu --set full captures are separate calls, tools/gpu_ncu_full.sh f64|f32: gpurun copies back at most 64 MiB per call)
 mkdir -p gpurun_out
 timeout 1500 python bench.py --steps 10000 --warmup 5 --no-cpu --no-disk > gpurun_out/r2_long_n1.json 2> gpurun_out/r2_long_n1.err
 python -c "import json;d=json.load(open('gpurun_out/r2_long_n1.json'));print('long n1',d['value'],d['ms_per_step'],d['clocks'],d['e2e']['value'])"
