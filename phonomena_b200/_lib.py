@@ -5,8 +5,10 @@ calls raise.  PyTorch is not needed here; NumPy arrays are the host buffers.
 """
 from __future__ import annotations
 
+import atexit
 import ctypes as C
 import os
+import weakref
 
 import numpy as np
 
@@ -166,6 +168,22 @@ def comm_unique_id():
     return buf.raw
 
 
+_live = weakref.WeakSet()
+
+
+def _close_all():
+    """Interpreter exit: destroy the contexts that are still alive NOW, while the CUDA runtime still is -- a context
+    destroyed from __del__ during interpreter teardown (after libcudart's own exit handlers) can crash the process."""
+    for e in list(_live):
+        try:
+            e.close()
+        except Exception:
+            pass
+
+
+atexit.register(_close_all)
+
+
 class Engine:
     """One device context = one grid or one x-slab [x0, x0+nxl) on one GPU."""
 
@@ -193,6 +211,7 @@ class Engine:
         self.record_mask = int(record_mask)
         self._ctx = C.c_void_p()
         _chk(self.lib, self.lib.phb_create(C.byref(cfg), C.byref(self._ctx)))
+        _live.add(self)
 
     # -- lifetime ---------------------------------------------------------------------
     def close(self):

@@ -24,6 +24,7 @@ To install into a Phonomena checkout, drop a three-line ``solver_b200.py`` into
 """
 from __future__ import annotations
 
+import atexit
 import copy
 import json
 import logging
@@ -38,6 +39,7 @@ from . import _lib, hostmath as hm
 from .h5lite import H5Writer, merge_slabs
 
 logger = logging.getLogger(__name__)
+_live_solvers = None      # weak set of Solver instances, closed at interpreter exit before the engines are (see _lib._close_all)
 
 # module-level cfg, merged with the base defaults like the reference plugins do
 # (solver_numba.py:8-13,22).  All values are JSON-serialisable (common.saveSettings dumps them).
@@ -205,6 +207,12 @@ class Solver:
         self.engine = None
         self.writer = None
         self.stats = {}
+        global _live_solvers
+        if _live_solvers is None:
+            import weakref
+            _live_solvers = weakref.WeakSet()
+            atexit.register(_close_solvers)
+        _live_solvers.add(self)
 
     # ------------------------------------------------------------------------------------
     def init(self, grid, material, steps):
@@ -532,6 +540,14 @@ class Solver:
     def __del__(self):
         try:
             self._close_engine()
+        except Exception:
+            pass
+
+
+def _close_solvers():
+    for s in list(_live_solvers or ()):
+        try:
+            s._close_engine()
         except Exception:
             pass
 
