@@ -871,14 +871,12 @@ struct Engine : IEngine {
             c->launches++;
         }
         if (c->halo == 2 && c->nranks > 1) {
-            // ONE stencil launch: the edge planes are pushed into the neighbours' ghost planes by the kernel itself;
-            // then a stream-ordered flag write / wait (no NCCL kernel, no SM taken from the stencil), and the y / z
-            // absorbing faces are applied to the owned planes AND to the received ghost planes (same formula and
-            // inputs as on the owning rank, so the result stays bit-identical).
+            // halo exchange over NVLink peer memory (CUDA IPC), no collective call; two modes (phb_p2p_mode)
             const bool hasL = c->rank > 0, hasR = c->rank < c->nranks - 1;
             if (!c->push_fused) {
-                // stencil (one launch, or the split pair) -> periodic fix-up -> all faces of the owned planes -> push the two
-                // finished edge planes into the neighbours' ghost planes + signal -> wait for the neighbours' signal
+                // default: wait for the neighbours' flags of the previous step (their edge planes are in my ghost planes) ->
+                // stencil (one launch, or the split parts) -> periodic fix-up -> all faces of the owned planes -> push the two
+                // finished edge planes into the neighbours' ghost planes, publish the step number, count the step
                 int *const fl = hasL ? c->flags + 0 : nullptr, *const fr = hasR ? c->flags + 1 : nullptr;
                 const int nxl = xe - x0, cl = (nxl + 3) / 4;
                 if (c->overlap && use_march() && nxl >= 384) {
@@ -921,6 +919,9 @@ struct Engine : IEngine {
                 CU(cudaGetLastError());
                 return 0;
             }
+            // mode "fused": ONE stencil launch pushes the edge planes into the neighbours' ghost planes itself; then a flag
+            // write / wait, and the y / z absorbing faces are applied to the owned planes AND to the received ghost planes
+            // (same formula and inputs as on the owning rank, so the result stays bit-identical)
             if (!use_march()) return fail("halo=fused needs the marching kernel");
             if (periodic_y()) return fail("periodic y boundaries: use halo mode p2p or nccl (the fix-up rows are final only after the stencil kernel)");
             OK(physics(x0, xe));
