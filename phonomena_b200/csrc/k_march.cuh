@@ -37,8 +37,12 @@
 //  * The reference's slice ranges ("never written => 0") are not code here: the per-cell
 //    stencil class (1 byte, fd_common.cuh) selects a 16-entry coefficient row in shared memory
 //    that is already zero wherever a stress or an update does not exist.
-//  * u_new leaves as 16-byte vector stores; with template ZF the block that owns k = nz-1 then applies
-//    the z = -1 absorbing face to its own results (three scalar re-stores by one lane).
+//  * u_new leaves as 16-byte vector stores; with template ZF the block that owns k = nz-1 first applies
+//    the z = -1 absorbing face to its own results (branch-free selects in the face lane).
+//  * Split step (phb200.cu physics()): a step is launched as up to three instantiations side by side, one per class
+//    of z-tiles -- the tile with k = 0 (K0 = true, EDGE = 1), the tiles between (K0 = false: no first-element
+//    selects), the tile that owns the face (ZF, K0 = false, EDGE = 2) -- so that no block carries code only another
+//    tile can need; blockIdx.x is offset by StepArgs::ztile0.
 //
 // Arithmetic goes through the same formula functions as the naive kernel, so in EXACT mode
 // both are bit-identical to the reference.
