@@ -14,7 +14,7 @@ step of the whole grid.  Synthetic, deterministic; all arrays are far larger tha
 
 One JSON line on rank 0:
   value      Gcell-updates/s, device-timed (CUDA events on the launching stream, max over ranks),
-             fields resident in HBM, production launch path (CUDA-graph replay on one GPU); the kernel
+             fields resident in HBM, production launch path (CUDA-graph replay of the step, slabs included); the kernel
              share for the roofline comes from a SECOND pass of K steps with per-launch event pairs
   parity     N > 1: before the timed region every rank checks its slabs of a small crystal, stepped through
              the same halo exchange, bit for bit against a single-GPU run (phonomena_b200/selfcheck.py);
@@ -22,7 +22,7 @@ One JSON line on rank 0:
   e2e        the same metric through the plugin API (Solver.init + Solver.run, reference interface),
              wall clock of run(): per step the source sample goes host->device and the recorded
              surface plane (uz at z-index 0, BASELINE config #3; --e2e-fields ux,uy,uz for all three)
-             comes device->pinned host->HDF5 file
+             comes device->pinned host->native writer threads->HDF5 file; over max(K, 200) steps; init() reported as init_s
   roofline   dominant kernel (k_step_march): algorithmic bytes (73 B/cell fp64: 9 field words + 1
              class byte) / measured kernel time, against MEASURED_PEAKS.json hbm_gbs
   cpu_baseline  the UNMODIFIED reference solver (oracle/_ref, staged by `make -C oracle ref`; kind "reference")
